@@ -1,0 +1,29 @@
+"""TEST INFRASTRUCTURE ONLY — CPU oracle for the SAMAudio.separate() hot path.
+
+Nothing under ``oracle/`` is product code.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the CPU-baseline / ``--impl reference`` legs of
+``bench.py`` may import it, and only as the checker / the CPU reference being
+timed.  The product package (``sam_audio_b200``) never imports it.
+
+Contents
+--------
+``restate.py``     fp32 torch restatement of the reference algorithm (each
+                   function cites the reference file:line it follows).
+``ref_loader.py``  imports the *unmodified* reference from /root/reference with
+                   ``sys.modules`` stubs for its absent third-party deps.  Only
+                   usable in the build container (the GPU box has no
+                   /root/reference); used by ``make_golden.py`` to pin
+                   ``restate.py`` and to generate ``tests/golden/*.pt``.
+``make_golden.py`` the committed generator of the golden fixtures.
+
+Parity status
+-------------
+* DiT / SAMAudio.forward / align / anchors / processor / ODE control flow:
+  PINNED — restate.py is checked against the reference's own modules run in
+  this container (see tests/test_oracle_golden.py and make_golden.py).
+* DAC-VAE codec arithmetic (third-party ``dacvae @ main``, source absent from
+  /root/reference), T5 numerics (``transformers``), torchdiffeq: PARITY
+  UNPINNED by the reference — restated from the published Descript-DAC layout
+  and the reference's call sites (codec.py:45-89, config.py:10-41); the CUDA
+  path is checked against this restatement only.
+"""
