@@ -1,0 +1,116 @@
+/* samaudio_b200.h — C ABI of libsamaudio_b200.so: the B200 (sm_100a) implementation of the
+ * SAMAudio.separate() inference hot path of facebookresearch/sam-audio.
+ *
+ * The reference has no FFI: its seam is the Python class surface.  Each entry point
+ * below names the reference method it replaces (paths relative to the reference tree); the Python
+ * host mirror (sam_audio_b200/model.py) and INTEGRATION.md show the binding.
+ *
+ * Conventions
+ *  - plain C types only; every device pointer is BORROWED (the caller — PyTorch in the Python mirror —
+ *    owns activations and I/O buffers); the library owns its packed weights and workspace.
+ *  - every function returns 0 on success, non-zero on failure; sab_last_error() gives the message
+ *    (reference convention is Python exceptions; the mirror raises RuntimeError from it).
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *    unless stated.  A handle is not thread-safe.
+ *  - layouts: "rows x cols" row-major, fp32 unless stated; T = latent frames (25 Hz), S = samples.
+ */
+#ifndef SAMAUDIO_B200_H
+#define SAMAUDIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sab_engine sab_engine;
+
+/* Shapes of the model (reference: sam_audio/model/config.py:86-130 TransformerConfig,
+ * :10-41 DACVAEConfig, :204-231 SAMAudioConfig). */
+typedef struct sab_config {
+  int32_t dim;              /* transformer.dim (multiple of 128)            */
+  int32_t n_heads;          /* transformer.n_heads (head_dim must be 128)   */
+  int32_t n_layers;         /* transformer.n_layers                         */
+  int32_t ffn_hidden;       /* SwiGLU hidden width (transformer.py:179-185) */
+  int32_t out_channels;     /* 256                                          */
+  int32_t in_channels;      /* SAMAudioConfig.in_channels = 768             */
+  int32_t text_dim;         /* 768                                          */
+  int32_t vision_dim;       /* 1024                                         */
+  int32_t n_anchor_tokens;  /* num_anchors + 1 = 4                          */
+  int32_t anchor_dim;       /* 128                                          */
+  int32_t max_positions;    /* RoPE table length (10000)                    */
+  float   rope_theta;       /* max(10000, 2*max_positions)                  */
+  float   norm_eps;         /* 1e-5                                         */
+  /* DAC-VAE codec */
+  int32_t codec_encoder_dim;      /* 64   */
+  int32_t codec_latent_dim;       /* 1024 */
+  int32_t codec_decoder_dim;      /* 1536 */
+  int32_t codec_codebook_dim;     /* 128  */
+  int32_t codec_n_rates;          /* 4    */
+  int32_t codec_encoder_rates[8]; /* 2,8,10,12 */
+  int32_t codec_decoder_rates[8]; /* 12,10,8,2 */
+} sab_config;
+
+const char* sab_last_error(void);
+int sab_version(void);
+
+/* Lifecycle.  replaces: SAMAudio.__init__ (model.py:79-102). */
+int sab_create(const sab_config* cfg, int device, sab_engine** out);
+int sab_destroy(sab_engine* e);
+
+/* Weights.  replaces: BaseModel._from_pretrained / load_state_dict (base.py:47-61, model.py:346-359).
+ * `name` is the reference state-dict key (e.g. "transformer.layers.0.attention.wq.weight"; codec keys
+ * "audio_codec.encoder.block.0.weight", weight-norm already folded).  `data` is fp32, contiguous, on host
+ * (is_device=0) or device (is_device=1); it is consumed (repacked to bf16 / permuted) before returning.
+ * Unknown names fail.  sab_finalize_weights() checks completeness and builds derived tables. */
+int sab_load_weight(sab_engine* e, const char* name, const float* data, const int64_t* shape, int ndim,
+                    int is_device, void* stream);
+int sab_finalize_weights(sab_engine* e, void* stream);
+
+/* Codec analysis.  replaces: DACVAE.forward (codec.py:65-78) + SAMAudio._get_audio_features (model.py:182-184).
+ * wav [B, S] mono fp32 (S already padded to a multiple of hop by the caller = codec.py:72-78);
+ * features [B, T, 2*codebook_dim] fp32: the 128-d mean latent duplicated along channels. */
+int sab_encode(sab_engine* e, const float* wav, int B, int64_t S, float* features, void* stream);
+
+/* Conditioning, once per separate() call.  replaces the time-independent part of SAMAudio.forward:
+ * align_inputs (model.py:108-128), AlignModalities (align.py:30-50), EmbedAnchors (model.py:54-65),
+ * memory_proj (model.py:92,172).
+ *  features       [Bc, T, 256]      (sab_encode output, already repeated per candidate)
+ *  text_features  [Bc, L, text_dim] ; text_mask [Bc, L] uint8 (1 = token)
+ *  video_features [Bc, vision_dim, T] or NULL (= zeros, model.py:188-189)
+ *  anchor_ids [Bc, n_ids] int64 ; anchor_alignment [Bc, T] int64 ; audio_pad_mask [Bc, T] uint8 (1 = frame) */
+int sab_prepare(sab_engine* e, int Bc, int T, int L, const float* features, const float* text_features,
+                const uint8_t* text_mask, const float* video_features, const int64_t* anchor_ids, int n_ids,
+                const int64_t* anchor_alignment, const uint8_t* audio_pad_mask, void* stream);
+
+/* One ODE function evaluation.  replaces: SAMAudio.forward / DiT.forward (model.py:130-180,
+ * transformer.py:473-524) on the conditioning installed by sab_prepare.
+ * noisy [Bc, T, 256], time [Bc] (device), velocity out [Bc, T, 256]. */
+int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float* velocity, void* stream);
+
+/* The ODE solve.  replaces: torchdiffeq.odeint(method="midpoint", step_size=1/n_steps) as called at
+ * model.py:285-290 (2*n_steps evaluations).  noise [Bc, T, 256] in, latent [Bc, T, 256] out (may alias). */
+int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, void* stream);
+
+/* Codec synthesis.  replaces: DACVAE.decode (codec.py:86-89) as called at model.py:291-295.
+ * latent [Bc, T, 256] (target half = channels [0,128), residual half = [128,256));
+ * wav [Bc, 2, T*hop] fp32 (row 0 target, row 1 residual). */
+int sab_decode(sab_engine* e, const float* latent, int Bc, int T, float* wav, void* stream);
+
+/* Introspection for benchmarks/tests: kernels launched by this engine since creation / last reset. */
+int64_t sab_launch_count(sab_engine* e, int reset);
+/* Workspace bytes currently held. */
+int64_t sab_workspace_bytes(sab_engine* e);
+
+/* ---- unit-test seams (used by tests/ only; stable but not part of the drop-in surface) ---- */
+/* C[M,N] (fp32) = A[M,K] (bf16) * B[N,K]^T (bf16) through the tcgen05 GEMM (BN = 128 or 256, BK = 64 or 32). */
+int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk,
+                  void* stream);
+/* O = softmax(Q K^T / sqrt(128) + mask) V through the attention kernel; all [items*T, heads*128] bf16. */
+int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, const void* k, const void* v,
+                       const uint8_t* key_mask, void* o, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMAUDIO_B200_H */

@@ -1,0 +1,277 @@
+// HBM-bound fused elementwise / reduction kernels of the DiT path (float4 loads, warp-shuffle reductions).
+// Each kernel cites the reference lines whose arithmetic it fuses.
+#pragma once
+#include "common.cuh"
+
+namespace sab {
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm + adaLN modulate  (transformer.py:42-47 RMSNorm fp32, :21-22 modulate, :375/:389/:513-515)
+//   out[m, :] = bf16( x[m,:] * rsqrt(mean(x^2)+eps) * w * (1 + scale[b,:]) + shift[b,:] ),  b = m / rows_per_item
+// one warp per row; the row stays in registers between the reduction and the write (single HBM read).
+// ---------------------------------------------------------------------------------------------
+template <int kVecPerLane>  // d = kVecPerLane * 128
+__global__ void __launch_bounds__(256)
+rmsnorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                   const float* __restrict__ scale, long long mod_ld, int rows_per_item,
+                   __nv_bfloat16* __restrict__ out, int M, float eps) {
+  constexpr int d = kVecPerLane * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  float4 v[kVecPerLane];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    v[i] = xr[lane + i * 32];
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)d + eps);
+  const long long b = row / rows_per_item;
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_ld);
+  const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_ld);
+  uint2* orow = reinterpret_cast<uint2*>(out + (long long)row * d);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int c = lane + i * 32;
+    const float4 ww = wr[c], s1 = sc[c], s0 = sh[c];
+    const float a = v[i].x * rstd * ww.x * (1.f + s1.x) + s0.x;
+    const float bb = v[i].y * rstd * ww.y * (1.f + s1.y) + s0.y;
+    const float cc = v[i].z * rstd * ww.z * (1.f + s1.z) + s0.z;
+    const float dd = v[i].w * rstd * ww.w * (1.f + s1.w) + s0.w;
+    orow[c] = make_uint2(pack_bf16(a, bb), pack_bf16(cc, dd));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaLN tables for one NFE  (transformer.py:363-371, :507-509):
+//   mod[l][b][r][:] = scale_shift_table_l[r][:] + t0[b][r*d : (r+1)*d],  r = 0..5
+//   fin[b][r][:]    = final_table[r][:] + t[b][:],                        r = 0..1
+// ---------------------------------------------------------------------------------------------
+__global__ void build_mod_kernel(const float* __restrict__ tables /*[L,6,d]*/, const float* __restrict__ t0 /*[B,6d]*/,
+                                 float* __restrict__ mod /*[L,B,6,d]*/, int L, int B, int d,
+                                 const float* __restrict__ ftable /*[2,d]*/, const float* __restrict__ t /*[B,d]*/,
+                                 float* __restrict__ fin /*[B,2,d]*/) {
+  const long long n_mod = (long long)L * B * 6 * d / 4;
+  const long long n_fin = (long long)B * 2 * d / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_mod + n_fin;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_mod) {
+      const long long e = i * 4;
+      const int c = (int)(e % (6 * d));
+      const int b = (int)((e / (6 * d)) % B);
+      const int l = (int)(e / ((long long)6 * d * B));
+      const float4 a = *reinterpret_cast<const float4*>(tables + (long long)l * 6 * d + c);
+      const float4 bb = *reinterpret_cast<const float4*>(t0 + (long long)b * 6 * d + c);
+      *reinterpret_cast<float4*>(mod + e) = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+    } else {
+      const long long e = (i - n_mod) * 4;
+      const int c = (int)(e % d);
+      const int r = (int)((e / d) % 2);
+      const int b = (int)(e / (2 * d));
+      const float4 a = *reinterpret_cast<const float4*>(ftable + r * d + c);
+      const float4 bb = *reinterpret_cast<const float4*>(t + (long long)b * d + c);
+      *reinterpret_cast<float4*>(fin + e) = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Timestep features (transformer.py:236-253: cat(cos,sin) of t*exp(-ln(1e4) i/128), raw t)  -> bf16 [B,256]
+// and the memory input (model.py:30-42,170-172: memory_proj(text) + cat(cos,sin)(t*exp(-ln(1e4) i/(d/2)))) -> bf16 [B*L,d]
+// ---------------------------------------------------------------------------------------------
+__global__ void time_features_kernel(const float* __restrict__ time /*[B]*/, int B, int d, int L,
+                                     __nv_bfloat16* __restrict__ tfreq /*[B,256]*/,
+                                     const float* __restrict__ mem_base /*[B*L,d]*/,
+                                     __nv_bfloat16* __restrict__ mem_in /*[B*L,d]*/) {
+  const long long n1 = (long long)B * 256, n2 = (long long)B * L * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n1 + n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int b = (int)(i / 256), c = (int)(i % 256);
+      const int k = c & 127;
+      const float f = expf(-logf(10000.f) * (float)k / 128.f);
+      const float a = time[b] * f;
+      tfreq[i] = __float2bfloat16(c < 128 ? cosf(a) : sinf(a));
+    } else {
+      const long long e = i - n1;
+      const int c = (int)(e % d);
+      const int b = (int)(e / ((long long)L * d));
+      const int half = d / 2;
+      const int k = c < half ? c : c - half;
+      const float f = expf(-logf(10000.f) * (float)k / (float)half);
+      const float a = time[b] * f;
+      mem_in[e] = __float2bfloat16(mem_base[e] + (c < half ? cosf(a) : sinf(a)));
+    }
+  }
+}
+
+// silu + cast (transformer.py:492 t_block_non_linearity) fp32 -> bf16
+__global__ void silu_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(silu_f(x[i]));
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(1 group) over the whole (T, C) slab of an item, then SiLU  (patcher.py:83-98, num_groups=1)
+// pass 1: per-item partial sums (double) ; pass 2: normalise + affine + SiLU -> bf16
+// ---------------------------------------------------------------------------------------------
+constexpr int GN_CHUNKS = 32;
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, long long n_per_item, double* __restrict__ partial /*[items,GN_CHUNKS,2]*/) {
+  const int item = blockIdx.y, chunk = blockIdx.x;
+  const long long n4 = n_per_item / 4;
+  const long long per = (n4 + GN_CHUNKS - 1) / GN_CHUNKS;
+  const long long lo = chunk * per, hi = (lo + per < n4) ? lo + per : n4;
+  const float4* xp = reinterpret_cast<const float4*>(x + item * n_per_item);
+  float s = 0.f, q = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float4 v = xp[i];
+    s += v.x + v.y + v.z + v.w;
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ double sh[2][8];
+  double ds = warp_sum(s), dq = warp_sum(q);
+  // (per-thread fp32 partials over <= a few thousand elements, then double across warps/chunks)
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ds; sh[1][threadIdx.x >> 5] = dq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; b += sh[1][i]; }
+    partial[((long long)item * GN_CHUNKS + chunk) * 2] = a;
+    partial[((long long)item * GN_CHUNKS + chunk) * 2 + 1] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_silu_kernel(const float* __restrict__ x, const double* __restrict__ partial, const float* __restrict__ gamma,
+               const float* __restrict__ beta, int C, long long n_per_item, float eps,
+               __nv_bfloat16* __restrict__ y) {
+  const int item = blockIdx.y;
+  __shared__ float s_mean, s_rstd;
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < GN_CHUNKS; ++i) {
+      a += partial[((long long)item * GN_CHUNKS + i) * 2];
+      b += partial[((long long)item * GN_CHUNKS + i) * 2 + 1];
+    }
+    const double mean = a / (double)n_per_item;
+    const double var = b / (double)n_per_item - mean * mean;
+    s_mean = (float)mean;
+    s_rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  const float4* xp = reinterpret_cast<const float4*>(x + item * n_per_item);
+  uint2* yp = reinterpret_cast<uint2*>(y + item * n_per_item);
+  const long long n4 = n_per_item / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = xp[i];
+    const int c = (int)((i * 4) % C);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 bb = *reinterpret_cast<const float4*>(beta + c);
+    const float a0 = silu_f((v.x - mean) * rstd * g.x + bb.x);
+    const float a1 = silu_f((v.y - mean) * rstd * g.y + bb.y);
+    const float a2 = silu_f((v.z - mean) * rstd * g.z + bb.z);
+    const float a3 = silu_f((v.w - mean) * rstd * g.w + bb.w);
+    yp[i] = make_uint2(pack_bf16(a0, a1), pack_bf16(a2, a3));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditioning finish, once per separate() call (time-independent part of align_inputs):
+//   cond[m,:] += tanh(g_v) * LayerNorm(vproj[m,:]) (or the constant vector for absent video)     align.py:41-50
+//             +  tanh(g_a) * E[ ids[b, align[b,t]] , :]        E = embed @ proj^T (4 x d)          model.py:63-65
+// one warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cond_finish_kernel(float* __restrict__ cond, int M, int d, int T,
+                   const float* __restrict__ vproj /*[M,d] or null*/, const float* __restrict__ ln_w,
+                   const float* __restrict__ ln_b, const float* __restrict__ vconst /*[d] (used when vproj null)*/,
+                   const float* __restrict__ gate_v, const float* __restrict__ anchor_table /*[n_anchor+1, d]*/,
+                   const long long* __restrict__ anchor_ids, int n_ids, const long long* __restrict__ anchor_align,
+                   const float* __restrict__ gate_a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int b = row / T, t = row % T;
+  const float gv = tanhf(gate_v[0]), ga = tanhf(gate_a[0]);
+  const long long slot = anchor_align[(long long)b * T + t];
+  const long long id = anchor_ids[(long long)b * n_ids + slot];
+  const float* er = anchor_table + id * d;
+  float* cr = cond + (long long)row * d;
+  float mean = 0.f, rstd = 0.f;
+  const float* vr = nullptr;
+  if (vproj) {
+    vr = vproj + (long long)row * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += vr[c];
+    mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+    for (int c = lane; c < d; c += 32) { const float u = vr[c] - mean; q += u * u; }
+    rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+  }
+  for (int c = lane; c < d; c += 32) {
+    const float vterm = vproj ? ((vr[c] - mean) * rstd * ln_w[c] + ln_b[c]) : vconst[c];
+    cr[c] += gv * vterm + ga * er[c];
+  }
+}
+
+// LayerNorm of a single vector (the conv bias) -> constant video term for text-only prompts
+__global__ void ln_vector_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                 int d, float* __restrict__ y) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s += x[c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float mean = tot / (float)d;
+  __syncthreads();
+  float q = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) { const float u = x[c] - mean; q += u * u; }
+  q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  __syncthreads();
+  float qt = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) qt += red[i];
+  const float rstd = rsqrtf(qt / (float)d + 1e-5f);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) y[c] = (x[c] - mean) * rstd * w[c] + b[c];
+}
+
+// small dense fp32 product for load-time tables: C[i,j] = sum_k A[i,k] * B[j,k]   (anchor table 4 x d)
+__global__ void small_abt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                 int I, int J, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I * J) return;
+  const int i = idx / J, j = idx % J;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s = fmaf(A[i * K + k], B[(long long)j * K + k], s);
+  C[idx] = s;
+}
+
+// RoPE table (rope.py:116-145): rope[pos][i] = (cos, sin)(pos * theta^(-2i/hd)), i < hd/2
+__global__ void rope_table_kernel(float2* __restrict__ rope, int T, int hd, float theta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * (hd / 2)) return;
+  const int pos = idx / (hd / 2), i = idx % (hd / 2);
+  const float inv = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
+  const float a = (float)pos * inv;
+  rope[idx] = make_float2(cosf(a), sinf(a));
+}
+
+// mask expansion helpers ------------------------------------------------------------------------
+__global__ void fill_kernel_f32(float* p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace sab

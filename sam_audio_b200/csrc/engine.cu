@@ -1,0 +1,1212 @@
+// libsamaudio_b200.so — engine + C ABI (include/samaudio_b200.h).
+// Weights are repacked to bf16 GEMM operands at load; every (Bc, T, L) shape gets a static plan
+// (workspace + TMA descriptors + launch records) that each ODE evaluation replays.
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <functional>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/samaudio_b200.h"
+#include "host_util.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "codec_kernels.cuh"
+
+using namespace sab;
+typedef __nv_bfloat16 bf16;
+
+static thread_local std::string g_last_error;
+static int g_sm_count = 0;
+
+// =====================================================================================================
+// GEMM dispatch
+// =====================================================================================================
+template <int BN, int BK, int MODE>
+static void launch_gemm_inst(const GemmOp& op, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, BK, MODE>;
+  if (!configured) {
+    SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BK>::kTotal));
+    configured = true;
+  }
+  kern<<<op.grid, GEMM_THREADS, GemmSmem<BN, BK>::kTotal, st>>>(op.tmA, op.tmB, op.P);
+  SAB_CUDA(cudaGetLastError());
+}
+
+static void launch_gemm(const GemmOp& op, cudaStream_t st) {
+#define SAB_CASE(bn, bk, md) \
+  if (op.BN == bn && op.BK == bk && op.mode == md) return launch_gemm_inst<bn, bk, md>(op, st);
+  SAB_CASE(256, 64, EPI_AFFINE)
+  SAB_CASE(192, 64, EPI_AFFINE)
+  SAB_CASE(128, 64, EPI_AFFINE)
+  SAB_CASE(96, 64, EPI_AFFINE)
+  SAB_CASE(64, 64, EPI_AFFINE)
+  SAB_CASE(96, 32, EPI_AFFINE)
+  SAB_CASE(128, 32, EPI_AFFINE)
+  SAB_CASE(256, 64, EPI_SWIGLU)
+  SAB_CASE(256, 64, EPI_QKV)
+  SAB_CASE(128, 64, EPI_QKV)
+#undef SAB_CASE
+  throw Error(fmt("no GEMM instantiation for BN=%d BK=%d mode=%d (%s)", op.BN, op.BK, op.mode, op.tag));
+}
+
+// A operand view
+struct AView {
+  const bf16* ptr;
+  int64_t cols;        // row width visible to TMA (elements)
+  int64_t rows;        // rows per item
+  int64_t items;
+  int64_t row_pitch;   // elements
+  int64_t item_pitch;  // elements
+};
+static AView flat_view(const bf16* p, int64_t M, int64_t K, int64_t ld = -1) {
+  return AView{p, K, M, 1, ld < 0 ? K : ld, 0};
+}
+static AView seq_view(const bf16* p, int64_t items, int64_t T, int64_t C) { return AView{p, C, T, items, C, T * C}; }
+
+struct RunList {
+  int n[2] = {0, 0};
+  KRun r[2][GEMM_MAX_RUNS];
+  int period = 0, sw = 0;
+  void add(int list, int shift, int col, int nkb) {
+    SAB_CHECK(n[list] < GEMM_MAX_RUNS, "too many K runs");
+    r[list][n[list]++] = KRun{shift, col, nkb};
+  }
+  int total_kb(int list) const {
+    int t = 0;
+    for (int i = 0; i < n[list]; ++i) t += r[list][i].nkb;
+    return t;
+  }
+};
+
+static GemmOp make_gemm(const char* tag, const AView& A, const bf16* B, int N, int BN, int BK, int mode,
+                        const RunList& runs) {
+  GemmOp op;
+  memset(&op.P, 0, sizeof(op.P));
+  op.tag = tag;
+  op.BN = BN; op.BK = BK; op.mode = mode;
+  const int ktot = runs.total_kb(0) * BK;
+  if (runs.period > 0) SAB_CHECK(runs.total_kb(1) * BK == ktot, "%s: run lists differ in K", tag);
+  op.tmA = make_tmap_3d(A.ptr, A.cols, A.rows, A.items, A.row_pitch, A.item_pitch == 0 ? A.rows * A.row_pitch : A.item_pitch,
+                        BK, GEMM_BM);
+  op.tmB = make_tmap_2d(B, ktot, N, ktot, BK, BN);
+  GemmParams& P = op.P;
+  P.rows_per_item = (int)A.rows;
+  P.n_items = (int)A.items;
+  P.tiles_per_item = (int)((A.rows + GEMM_BM - 1) / GEMM_BM);
+  P.N = N;
+  P.n_tiles_n = (N + BN - 1) / BN;
+  for (int l = 0; l < 2; ++l) {
+    P.n_runs[l] = runs.n[l];
+    for (int i = 0; i < runs.n[l]; ++i) P.runs[l][i] = runs.r[l][i];
+  }
+  P.n_period = runs.period;
+  P.n_switch = runs.sw;
+  if (runs.period > 0) SAB_CHECK(runs.sw % BN == 0 && runs.period % BN == 0, "%s: BN=%d does not divide the tap switch %d/%d", tag, BN, runs.sw, runs.period);
+  P.alpha = 1.f;
+  P.gate_div = 1;
+  P.eps = 1e-5f;
+  const long long tiles = (long long)P.n_items * P.tiles_per_item * P.n_tiles_n;
+  op.grid = (int)std::min<long long>(tiles, g_sm_count);
+  op.flops = 2.0 * (double)A.rows * (double)A.items * (double)N * (double)ktot;
+  SAB_CHECK(N % 32 == 0, "%s: N=%d must be a multiple of 32", tag, N);
+  return op;
+}
+static GemmOp make_linear(const char* tag, const bf16* A, int64_t M, int K, const bf16* B, int N, int BN, int mode,
+                          int64_t lda = -1) {
+  SAB_CHECK(K % 64 == 0, "%s: K=%d must be a multiple of 64", tag, K);
+  RunList rl;
+  rl.add(0, 0, 0, K / 64);
+  return make_gemm(tag, flat_view(A, M, K, lda), B, N, BN, 64, mode, rl);
+}
+
+// =====================================================================================================
+// weight packing kernels
+// =====================================================================================================
+enum RowMap { ROW_IDENT = 0, ROW_HEADS = 1, ROW_SWIGLU_A = 2, ROW_SWIGLU_B = 3 };
+
+// dst[(row0 + map(r)) * ld + col0 + c] = bf16(src[r*rs + c*cs])
+__global__ void pack_bf16_kernel(bf16* __restrict__ dst, long long ld, long long row0, long long col0,
+                                 const float* __restrict__ src, long long R, long long C, long long rs, long long cs,
+                                 int rowmap, int H) {
+  const long long n = R * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C, c = i % C;
+    long long pr = r;
+    if (rowmap == ROW_HEADS) { const long long dd = r / H, h = r % H; pr = h * (R / H) + dd; }
+    else if (rowmap == ROW_SWIGLU_A) pr = (r >> 5) * 64 + (r & 31);
+    else if (rowmap == ROW_SWIGLU_B) pr = (r >> 5) * 64 + 32 + (r & 31);
+    dst[(row0 + pr) * ld + col0 + c] = __float2bfloat16(src[r * rs + c * cs]);
+  }
+}
+static void pack(bf16* dst, long long ld, long long row0, long long col0, const float* src, long long R, long long C,
+                 long long rs, long long cs, int rowmap, int H, cudaStream_t st) {
+  const long long n = R * C;
+  const int grid = (int)std::min<long long>((n + 255) / 256, 4096);
+  pack_bf16_kernel<<<grid, 256, 0, st>>>(dst, ld, row0, col0, src, R, C, rs, cs, rowmap, H);
+  SAB_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// engine state
+// =====================================================================================================
+struct Slot {
+  std::vector<int64_t> shape;
+  std::function<void(const float*, cudaStream_t)> load;
+  bool loaded = false;
+};
+
+struct LayerW {
+  bf16 *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *w13, *w2;
+  float *qn, *kn, *qn_c, *kn_c, *attn_norm, *ffn_norm;
+};
+
+struct ConvLayer {   // a multi-channel codec conv lowered to the GEMM
+  bf16* w = nullptr;
+  float* bias = nullptr;
+  int cin = 0, cout = 0, k = 0, stride = 1, dil = 1;
+  bool transposed = false;
+};
+struct ResUnitW {
+  float* a0; ConvLayer c7; float* a1; ConvLayer c1;
+};
+struct EncBlockW { ResUnitW ru[3]; float* a_down; ConvLayer down; int cin, cout, stride; };
+struct DecBlockW { float* a_up; ConvLayer up; ResUnitW ru[3]; int cin, cout, stride; };
+
+struct DitPlan;
+struct CodecPlan;
+
+struct sab_engine {
+  sab_config cfg;
+  int device = 0;
+  DevicePool wpool;
+  std::unordered_map<std::string, Slot> slots;
+  float* staging = nullptr;
+  int64_t staging_elems = 0;
+  bool finalized = false;
+  int64_t launches = 0;
+
+  // --- DiT weights ---
+  std::vector<LayerW> layers;
+  float* tables = nullptr;          // [L, 6, d]
+  bf16 *wp_y, *wp_f, *wmem, *wvid;  // proj (noisy third / feature third), memory_proj, align conv
+  float *proj_b, *mem_b, *vid_b, *vid_ln_w, *vid_ln_b, *vid_gate, *vid_const;
+  float *anchor_embed, *anchor_proj, *anchor_gate, *anchor_table;
+  bf16 *xe_w[2]; float *xe_b[2], *xe_gn_w[2], *xe_gn_b[2];
+  bf16 *t_w13, *t_w2, *tb_w, *y_w13, *y_w2, *w_out;
+  float *tb_b, *final_norm, *final_table;
+  float2* rope = nullptr;
+  int rope_len = 0;
+
+  // --- codec weights ---
+  float *enc0_w, *enc0_b;                 // Conv1d(1, C0, 7)
+  std::vector<EncBlockW> enc_blocks;
+  float* enc_final_alpha; ConvLayer enc_final;   // Snake + Conv k3
+  ConvLayer in_proj, out_proj;            // in_proj packed as [2*cz, latent] (mean rows duplicated)
+  ConvLayer dec0;                         // Conv k7 latent -> decoder_dim
+  std::vector<DecBlockW> dec_blocks;
+  float* dec_final_alpha; float *dec_last_w, *dec_last_b;  // Snake + Conv1d(C,1,7) + tanh
+
+  std::unique_ptr<DitPlan> dit;
+  std::map<std::pair<int, long long>, std::unique_ptr<CodecPlan>> enc_plans, dec_plans;
+
+  ~sab_engine();
+};
+
+static inline void count(sab_engine* e, int n = 1) { e->launches += n; }
+
+// =====================================================================================================
+// weight registry
+// =====================================================================================================
+static void reg(sab_engine* e, const std::string& name, std::vector<int64_t> shape,
+                std::function<void(const float*, cudaStream_t)> fn) {
+  Slot s;
+  s.shape = std::move(shape);
+  s.load = std::move(fn);
+  e->slots[name] = std::move(s);
+}
+static void reg_f32(sab_engine* e, const std::string& name, std::vector<int64_t> shape, float** dst) {
+  int64_t n = 1;
+  for (auto v : shape) n *= v;
+  *dst = e->wpool.alloc<float>(n, true);
+  float* d = *dst;
+  reg(e, name, shape, [d, n](const float* src, cudaStream_t st) {
+    SAB_CUDA(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  });
+}
+// plain [out, in] linear -> bf16 [out, in] (optionally a column window of the source)
+static void reg_linear(sab_engine* e, const std::string& name, int out, int in, bf16** dst, int rowmap = ROW_IDENT,
+                       int H = 1, bf16* into = nullptr, long long row0 = 0, long long ld = -1, int src_col0 = 0,
+                       int src_cols = -1) {
+  const int cols = src_cols < 0 ? in : src_cols;
+  if (!into) { *dst = e->wpool.alloc<bf16>((int64_t)out * cols, true); into = *dst; }
+  if (ld < 0) ld = cols;
+  reg(e, name, {out, in}, [=](const float* src, cudaStream_t st) {
+    pack(into, ld, row0, 0, src + src_col0, out, cols, in, 1, rowmap, H, st);
+  });
+}
+// Conv1d weight [co, ci, k] -> bf16 [co, k*ci] (tap-major K)
+static void reg_conv(sab_engine* e, const std::string& name, ConvLayer* L, int co, int ci, int k, int stride, int dil) {
+  L->cin = ci; L->cout = co; L->k = k; L->stride = stride; L->dil = dil; L->transposed = false;
+  L->w = e->wpool.alloc<bf16>((int64_t)co * ci * k, true);
+  bf16* w = L->w;
+  reg(e, name + ".weight", {co, ci, k}, [=](const float* src, cudaStream_t st) {
+    for (int kk = 0; kk < k; ++kk) pack(w, (long long)k * ci, 0, (long long)kk * ci, src + kk, co, ci, (long long)ci * k, k, ROW_IDENT, 1, st);
+  });
+  reg_f32(e, name + ".bias", {co}, &L->bias);
+}
+// ConvTranspose1d weight [ci, co, 2s] (stride s, padding s/2) -> bf16 [s*co, 2*ci]:
+// output sample r*s+u is x[r] * W[:, :, u+p] + (u < s/2 ? x[r-1] * W[:, :, u+p+s] : x[r+1] * W[:, :, u+p-s])
+static void reg_convT(sab_engine* e, const std::string& name, ConvLayer* L, int ci, int co, int s) {
+  SAB_CHECK(s % 2 == 0, "codec rates must be even (got %d)", s);
+  L->cin = ci; L->cout = co; L->k = 2 * s; L->stride = s; L->dil = 1; L->transposed = true;
+  L->w = e->wpool.alloc<bf16>((int64_t)s * co * 2 * ci, true);
+  bf16* w = L->w;
+  const int K = 2 * s, p = s / 2;
+  reg(e, name + ".weight", {ci, co, K}, [=](const float* src, cudaStream_t st) {
+    for (int u = 0; u < s; ++u) {
+      const int k0 = u + p;
+      const int k1 = (u < s / 2) ? u + p + s : u + p - s;
+      pack(w, 2LL * ci, (long long)u * co, 0, src + k0, co, ci, K, (long long)co * K, ROW_IDENT, 1, st);
+      pack(w, 2LL * ci, (long long)u * co, ci, src + k1, co, ci, K, (long long)co * K, ROW_IDENT, 1, st);
+    }
+  });
+  reg_f32(e, name + ".bias", {co}, &L->bias);
+}
+static void reg_resunit(sab_engine* e, const std::string& p, ResUnitW* R, int c, int dil) {
+  reg_f32(e, p + ".block.0.alpha", {1, c, 1}, &R->a0);
+  reg_conv(e, p + ".block.1", &R->c7, c, c, 7, 1, dil);
+  reg_f32(e, p + ".block.2.alpha", {1, c, 1}, &R->a1);
+  reg_conv(e, p + ".block.3", &R->c1, c, c, 1, 1, 1);
+}
+
+static void register_weights(sab_engine* e) {
+  const sab_config& c = e->cfg;
+  const int d = c.dim, H = c.n_heads, hid = c.ffn_hidden, L = c.n_layers;
+  auto S = [](const char* f, int i) { return fmt(f, i); };
+  // ---- conditioning ----
+  e->wp_y = e->wpool.alloc<bf16>((int64_t)d * 256, true);
+  e->wp_f = e->wpool.alloc<bf16>((int64_t)d * 256, true);
+  SAB_CHECK(c.in_channels == 768 && c.out_channels == 256, "in_channels/out_channels must be 768/256");
+  {
+    bf16 *wy = e->wp_y, *wf = e->wp_f;
+    const int in = c.in_channels;
+    reg(e, "proj.weight", {d, in}, [=](const float* src, cudaStream_t st) {
+      pack(wy, 256, 0, 0, src, d, 256, in, 1, ROW_IDENT, 1, st);         // multiplies the noisy latent
+      pack(wf, 256, 0, 0, src + 512, d, 256, in, 1, ROW_IDENT, 1, st);   // multiplies the mixture features
+    });
+  }
+  reg_f32(e, "proj.bias", {d}, &e->proj_b);
+  reg_linear(e, "memory_proj.weight", d, c.text_dim, &e->wmem);
+  reg_f32(e, "memory_proj.bias", {d}, &e->mem_b);
+  e->wvid = e->wpool.alloc<bf16>((int64_t)d * c.vision_dim, true);
+  {
+    bf16* wv = e->wvid;
+    const int vd = c.vision_dim;
+    reg(e, "align_masked_video.conv.weight", {d, vd, 1}, [=](const float* src, cudaStream_t st) {
+      pack(wv, vd, 0, 0, src, d, vd, vd, 1, ROW_IDENT, 1, st);
+    });
+  }
+  reg_f32(e, "align_masked_video.conv.bias", {d}, &e->vid_b);
+  reg_f32(e, "align_masked_video.layer_norm.weight", {d}, &e->vid_ln_w);
+  reg_f32(e, "align_masked_video.layer_norm.bias", {d}, &e->vid_ln_b);
+  reg_f32(e, "align_masked_video.gate", {1}, &e->vid_gate);
+  reg_f32(e, "embed_anchors.embed.weight", {c.n_anchor_tokens, c.anchor_dim}, &e->anchor_embed);
+  reg_f32(e, "embed_anchors.proj.weight", {d, c.anchor_dim}, &e->anchor_proj);
+  reg_f32(e, "embed_anchors.gate", {1}, &e->anchor_gate);
+  e->vid_const = e->wpool.alloc<float>(d, true);
+  e->anchor_table = e->wpool.alloc<float>((int64_t)c.n_anchor_tokens * d, true);
+  // ---- DiT prologue / epilogue ----
+  for (int b = 0; b < 2; ++b) {
+    const std::string p = fmt("transformer.x_embedder.block.block%d", b + 1);
+    reg_f32(e, p + ".groupnorm.weight", {d}, &e->xe_gn_w[b]);
+    reg_f32(e, p + ".groupnorm.bias", {d}, &e->xe_gn_b[b]);
+    e->xe_w[b] = e->wpool.alloc<bf16>((int64_t)d * 3 * d, true);
+    bf16* w = e->xe_w[b];
+    reg(e, p + ".project.weight", {d, d, 3}, [=](const float* src, cudaStream_t st) {
+      for (int k = 0; k < 3; ++k) pack(w, 3LL * d, 0, (long long)k * d, src + k, d, d, 3LL * d, 3, ROW_IDENT, 1, st);
+    });
+    reg_f32(e, p + ".project.bias", {d}, &e->xe_b[b]);
+  }
+  e->t_w13 = e->wpool.alloc<bf16>((int64_t)2 * d * 256, true);
+  reg_linear(e, "transformer.t_embedder.projection.w1.weight", d, 256, nullptr, ROW_SWIGLU_A, 1, e->t_w13, 0, 256);
+  reg_linear(e, "transformer.t_embedder.projection.w3.weight", d, 256, nullptr, ROW_SWIGLU_B, 1, e->t_w13, 0, 256);
+  reg_linear(e, "transformer.t_embedder.projection.w2.weight", d, d, &e->t_w2);
+  reg_linear(e, "transformer.t_block.weight", 6 * d, d, &e->tb_w);
+  reg_f32(e, "transformer.t_block.bias", {6 * d}, &e->tb_b);
+  e->y_w13 = e->wpool.alloc<bf16>((int64_t)2 * d * d, true);
+  reg_linear(e, "transformer.y_embedder.projection.w1.weight", d, d, nullptr, ROW_SWIGLU_A, 1, e->y_w13, 0, d);
+  reg_linear(e, "transformer.y_embedder.projection.w3.weight", d, d, nullptr, ROW_SWIGLU_B, 1, e->y_w13, 0, d);
+  reg_linear(e, "transformer.y_embedder.projection.w2.weight", d, d, &e->y_w2);
+  reg_f32(e, "transformer.norm.weight", {d}, &e->final_norm);
+  reg_linear(e, "transformer.output.weight", c.out_channels, d, &e->w_out);
+  reg_f32(e, "transformer.final_layer_scale_shift_table", {2, d}, &e->final_table);
+  // ---- DiT layers ----
+  e->tables = e->wpool.alloc<float>((int64_t)L * 6 * d, true);
+  e->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    LayerW& W = e->layers[l];
+    const std::string p = S("transformer.layers.%d", l);
+    W.wqkv = e->wpool.alloc<bf16>((int64_t)3 * d * d, true);
+    reg_linear(e, p + ".attention.wq.weight", d, d, nullptr, ROW_HEADS, H, W.wqkv, 0, d);
+    reg_linear(e, p + ".attention.wk.weight", d, d, nullptr, ROW_HEADS, H, W.wqkv, d, d);
+    reg_linear(e, p + ".attention.wv.weight", d, d, nullptr, ROW_HEADS, H, W.wqkv, 2 * d, d);
+    reg_linear(e, p + ".attention.wo.weight", d, d, &W.wo);
+    reg_f32(e, p + ".attention.q_norm.weight", {128}, &W.qn);
+    reg_f32(e, p + ".attention.k_norm.weight", {128}, &W.kn);
+    reg_linear(e, p + ".cross_attention.wq.weight", d, d, &W.wq_c, ROW_HEADS, H);
+    W.wkv_c = e->wpool.alloc<bf16>((int64_t)2 * d * d, true);
+    reg_linear(e, p + ".cross_attention.wk.weight", d, d, nullptr, ROW_HEADS, H, W.wkv_c, 0, d);
+    reg_linear(e, p + ".cross_attention.wv.weight", d, d, nullptr, ROW_HEADS, H, W.wkv_c, d, d);
+    reg_linear(e, p + ".cross_attention.wo.weight", d, d, &W.wo_c);
+    reg_f32(e, p + ".cross_attention.q_norm.weight", {128}, &W.qn_c);
+    reg_f32(e, p + ".cross_attention.k_norm.weight", {128}, &W.kn_c);
+    W.w13 = e->wpool.alloc<bf16>((int64_t)2 * hid * d, true);
+    reg_linear(e, p + ".feed_forward.w1.weight", hid, d, nullptr, ROW_SWIGLU_A, 1, W.w13, 0, d);
+    reg_linear(e, p + ".feed_forward.w3.weight", hid, d, nullptr, ROW_SWIGLU_B, 1, W.w13, 0, d);
+    reg_linear(e, p + ".feed_forward.w2.weight", d, hid, &W.w2);
+    reg_f32(e, p + ".attention_norm.weight", {d}, &W.attn_norm);
+    reg_f32(e, p + ".ffn_norm.weight", {d}, &W.ffn_norm);
+    float* tab = e->tables + (int64_t)l * 6 * d;
+    reg(e, p + ".scale_shift_table", {6, d}, [=](const float* src, cudaStream_t st) {
+      SAB_CUDA(cudaMemcpyAsync(tab, src, 6LL * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    });
+  }
+  // ---- codec ----
+  const std::string E = "audio_codec.encoder", D = "audio_codec.decoder", Q = "audio_codec.quantizer";
+  const int nr = c.codec_n_rates;
+  int ch = c.codec_encoder_dim;
+  SAB_CHECK(ch % 64 == 0, "codec encoder_dim must be a multiple of 64");
+  reg_f32(e, E + ".block.0.weight", {ch, 1, 7}, &e->enc0_w);
+  reg_f32(e, E + ".block.0.bias", {ch}, &e->enc0_b);
+  e->enc_blocks.resize(nr);
+  for (int i = 0; i < nr; ++i) {
+    EncBlockW& B = e->enc_blocks[i];
+    const int s = c.codec_encoder_rates[i];
+    SAB_CHECK(s % 2 == 0, "codec rates must be even");
+    B.cin = ch; B.cout = 2 * ch; B.stride = s;
+    const std::string p = fmt("%s.block.%d", E.c_str(), i + 1);
+    const int dil[3] = {1, 3, 9};
+    for (int j = 0; j < 3; ++j) reg_resunit(e, fmt("%s.block.%d", p.c_str(), j), &B.ru[j], ch, dil[j]);
+    reg_f32(e, p + ".block.3.alpha", {1, ch, 1}, &B.a_down);
+    reg_conv(e, p + ".block.4", &B.down, 2 * ch, ch, 2 * s, s, 1);
+    ch *= 2;
+  }
+  reg_f32(e, fmt("%s.block.%d.alpha", E.c_str(), nr + 1), {1, ch, 1}, &e->enc_final_alpha);
+  reg_conv(e, fmt("%s.block.%d", E.c_str(), nr + 2), &e->enc_final, c.codec_latent_dim, ch, 3, 1, 1);
+  {
+    // in_proj: only the mean half is used (codec.py:68); packed twice so one GEMM writes [.., 2*cz]
+    const int cz = c.codec_codebook_dim, ld = c.codec_latent_dim;
+    ConvLayer& P = e->in_proj;
+    P.cin = ld; P.cout = 2 * cz; P.k = 1;
+    P.w = e->wpool.alloc<bf16>((int64_t)2 * cz * ld, true);
+    P.bias = e->wpool.alloc<float>(2 * cz, true);
+    bf16* w = P.w; float* bptr = P.bias;
+    reg(e, Q + ".in_proj.weight", {2 * cz, ld, 1}, [=](const float* src, cudaStream_t st) {
+      pack(w, ld, 0, 0, src, cz, ld, ld, 1, ROW_IDENT, 1, st);
+      pack(w, ld, cz, 0, src, cz, ld, ld, 1, ROW_IDENT, 1, st);
+    });
+    reg(e, Q + ".in_proj.bias", {2 * cz}, [=](const float* src, cudaStream_t st) {
+      SAB_CUDA(cudaMemcpyAsync(bptr, src, cz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      SAB_CUDA(cudaMemcpyAsync(bptr + cz, src, cz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    });
+    reg_conv(e, Q + ".out_proj", &e->out_proj, ld, cz, 1, 1, 1);
+  }
+  int dch = c.codec_decoder_dim;
+  reg_conv(e, D + ".model.0", &e->dec0, dch, c.codec_latent_dim, 7, 1, 1);
+  e->dec_blocks.resize(nr);
+  for (int i = 0; i < nr; ++i) {
+    DecBlockW& B = e->dec_blocks[i];
+    const int s = c.codec_decoder_rates[i];
+    B.cin = dch; B.cout = dch / 2; B.stride = s;
+    const std::string p = fmt("%s.model.%d", D.c_str(), i + 1);
+    reg_f32(e, p + ".block.0.alpha", {1, dch, 1}, &B.a_up);
+    reg_convT(e, p + ".block.1", &B.up, dch, dch / 2, s);
+    const int dil[3] = {1, 3, 9};
+    for (int j = 0; j < 3; ++j) reg_resunit(e, fmt("%s.block.%d", p.c_str(), j + 2), &B.ru[j], dch / 2, dil[j]);
+    dch /= 2;
+  }
+  reg_f32(e, fmt("%s.model.%d.alpha", D.c_str(), nr + 1), {1, dch, 1}, &e->dec_final_alpha);
+  reg_f32(e, fmt("%s.model.%d.weight", D.c_str(), nr + 2), {1, dch, 7}, &e->dec_last_w);
+  reg_f32(e, fmt("%s.model.%d.bias", D.c_str(), nr + 2), {1}, &e->dec_last_b);
+}
+
+// =====================================================================================================
+// DiT plan: workspace + launch records for one (Bc, T, L)
+// =====================================================================================================
+struct LayerOps {
+  GemmOp qkv, wo, q_c, kv_c, wo_c, w13, w2;
+};
+struct DitPlan {
+  int Bc = 0, T = 0, L = 0;
+  int64_t M = 0, ML = 0;
+  DevicePool pool;
+  // activations
+  float *y, *ymid, *cond, *x0, *c1, *h, *t, *t0, *mod, *fin, *mem_base, *time_dev, *vproj;
+  bf16 *y_bf, *gn_a, *hb, *xn, *qkv, *att, *qc, *kvc, *u, *tfreq, *t_h, *t_silu, *mem_in, *y_h, *ymem, *feat_bf,
+      *text_bf, *vid_bf;
+  double* gn_partial;
+  uint8_t *pad_mask, *text_mask;
+  long long *anchor_ids, *anchor_align;
+  int n_ids_cap = 0;
+  // ops
+  GemmOp g_t13, g_t2, g_tb, g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid;
+  std::vector<LayerOps> lay;
+  double flops_per_eval = 0;
+};
+
+static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
+  const sab_config& c = e->cfg;
+  const int d = c.dim, hid = c.ffn_hidden, NL = c.n_layers;
+  auto P = std::make_unique<DitPlan>();
+  DitPlan& p = *P;
+  p.Bc = Bc; p.T = T; p.L = L;
+  const int64_t M = (int64_t)Bc * T, ML = (int64_t)Bc * L;
+  p.M = M; p.ML = ML;
+  SAB_CHECK(T <= e->rope_len, "T=%d exceeds the RoPE table (%d)", T, e->rope_len);
+  DevicePool& w = p.pool;
+  p.y = w.alloc<float>(M * 256); p.ymid = w.alloc<float>(M * 256);
+  p.cond = w.alloc<float>(M * d); p.x0 = w.alloc<float>(M * d); p.c1 = w.alloc<float>(M * d);
+  p.h = w.alloc<float>(M * d); p.vproj = w.alloc<float>(M * d);
+  p.t = w.alloc<float>((int64_t)Bc * d); p.t0 = w.alloc<float>((int64_t)Bc * 6 * d);
+  p.mod = w.alloc<float>((int64_t)NL * Bc * 6 * d); p.fin = w.alloc<float>((int64_t)Bc * 2 * d);
+  p.mem_base = w.alloc<float>(ML * d);
+  p.time_dev = w.alloc<float>((int64_t)Bc * 64);
+  p.y_bf = w.alloc<bf16>(M * 256); p.gn_a = w.alloc<bf16>(M * d); p.hb = w.alloc<bf16>(M * d);
+  p.xn = w.alloc<bf16>(M * d); p.qkv = w.alloc<bf16>(M * 3 * d); p.att = w.alloc<bf16>(M * d);
+  p.qc = w.alloc<bf16>(M * d); p.kvc = w.alloc<bf16>(ML * 2 * d); p.u = w.alloc<bf16>(M * hid);
+  p.tfreq = w.alloc<bf16>((int64_t)Bc * 256); p.t_h = w.alloc<bf16>((int64_t)Bc * d);
+  p.t_silu = w.alloc<bf16>((int64_t)Bc * d);
+  p.mem_in = w.alloc<bf16>(ML * d); p.y_h = w.alloc<bf16>(ML * d); p.ymem = w.alloc<bf16>(ML * d);
+  p.feat_bf = w.alloc<bf16>(M * 256); p.text_bf = w.alloc<bf16>(ML * c.text_dim);
+  p.vid_bf = w.alloc<bf16>(M * c.vision_dim);
+  p.gn_partial = w.alloc<double>((int64_t)Bc * GN_CHUNKS * 2);
+  p.pad_mask = w.alloc<uint8_t>(M); p.text_mask = w.alloc<uint8_t>(ML);
+  p.n_ids_cap = 64;
+  p.anchor_ids = w.alloc<long long>((int64_t)Bc * p.n_ids_cap); p.anchor_align = w.alloc<long long>(M);
+
+  // ---- once-per-call conditioning GEMMs ----
+  p.g_cond = make_linear("cond.proj_feat", p.feat_bf, M, 256, e->wp_f, d, 256, EPI_AFFINE);
+  p.g_cond.P.bias = e->proj_b; p.g_cond.P.out_f32 = p.cond; p.g_cond.P.out_f32_ld = d;
+  p.g_mem = make_linear("cond.memory_proj", p.text_bf, ML, c.text_dim, e->wmem, d, 256, EPI_AFFINE);
+  p.g_mem.P.bias = e->mem_b; p.g_mem.P.out_f32 = p.mem_base; p.g_mem.P.out_f32_ld = d;
+  p.g_vid = make_linear("cond.align_video", p.vid_bf, M, c.vision_dim, e->wvid, d, 256, EPI_AFFINE);
+  p.g_vid.P.bias = e->vid_b; p.g_vid.P.out_f32 = p.vproj; p.g_vid.P.out_f32_ld = d;
+
+  // ---- per-evaluation prologue ----
+  p.g_t13 = make_linear("t_embedder.w13", p.tfreq, Bc, 256, e->t_w13, 2 * d, 256, EPI_SWIGLU);
+  p.g_t13.P.out_bf16 = p.t_h; p.g_t13.P.out_bf16_ld = d;
+  p.g_t2 = make_linear("t_embedder.w2", p.t_h, Bc, d, e->t_w2, d, 256, EPI_AFFINE);
+  p.g_t2.P.out_f32 = p.t; p.g_t2.P.out_f32_ld = d;
+  p.g_tb = make_linear("t_block", p.t_silu, Bc, d, e->tb_w, 6 * d, 256, EPI_AFFINE);
+  p.g_tb.P.bias = e->tb_b; p.g_tb.P.out_f32 = p.t0; p.g_tb.P.out_f32_ld = 6 * d;
+  p.g_y13 = make_linear("y_embedder.w13", p.mem_in, ML, d, e->y_w13, 2 * d, 256, EPI_SWIGLU);
+  p.g_y13.P.out_bf16 = p.y_h; p.g_y13.P.out_bf16_ld = d;
+  p.g_y2 = make_linear("y_embedder.w2", p.y_h, ML, d, e->y_w2, d, 256, EPI_AFFINE);
+  p.g_y2.P.out_bf16 = p.ymem; p.g_y2.P.out_bf16_ld = d;
+  p.g_in = make_linear("proj.noisy", p.y_bf, M, 256, e->wp_y, d, 256, EPI_AFFINE);
+  p.g_in.P.res = p.cond; p.g_in.P.res_ld = d; p.g_in.P.out_f32 = p.x0; p.g_in.P.out_f32_ld = d;
+  for (int b = 0; b < 2; ++b) {
+    RunList rl;   // Conv1d k=3, zero padding (1,1): taps t-1, t, t+1  (patcher.py:52-67)
+    for (int k = 0; k < 3; ++k) rl.add(0, k - 1, 0, d / 64);
+    p.g_xe[b] = make_gemm(b == 0 ? "x_embedder.conv1" : "x_embedder.conv2", seq_view(p.gn_a, Bc, T, d), e->xe_w[b], d,
+                          256, 64, EPI_AFFINE, rl);
+    p.g_xe[b].P.bias = e->xe_b[b];
+    p.g_xe[b].P.out_f32 = b == 0 ? p.c1 : p.h; p.g_xe[b].P.out_f32_ld = d;
+    if (b == 1) { p.g_xe[b].P.res = p.x0; p.g_xe[b].P.res_ld = d; }
+  }
+  // ---- layers ----
+  p.lay.resize(NL);
+  for (int l = 0; l < NL; ++l) {
+    const LayerW& W = e->layers[l];
+    LayerOps& o = p.lay[l];
+    float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
+    o.qkv = make_linear("attention.qkv", p.xn, M, d, W.wqkv, 3 * d, 256, EPI_QKV);
+    o.qkv.P.out_bf16 = p.qkv; o.qkv.P.out_bf16_ld = 3 * d;
+    o.qkv.P.qnorm_w = W.qn; o.qkv.P.knorm_w = W.kn; o.qkv.P.n_q_end = d; o.qkv.P.n_k_end = 2 * d;
+    o.qkv.P.rope = e->rope; o.qkv.P.rope_T = T; o.qkv.P.use_rope = 1; o.qkv.P.eps = c.norm_eps;
+    o.wo = make_linear("attention.wo", p.att, M, d, W.wo, d, 256, EPI_AFFINE);
+    o.wo.P.gate = mod_l + 2 * d; o.wo.P.gate_ld = 6 * d; o.wo.P.gate_div = T;
+    o.wo.P.res = p.h; o.wo.P.res_ld = d; o.wo.P.out_f32 = p.h; o.wo.P.out_f32_ld = d;
+    o.wo.P.out_bf16 = p.hb; o.wo.P.out_bf16_ld = d;
+    o.q_c = make_linear("cross.wq", p.hb, M, d, W.wq_c, d, 256, EPI_QKV);
+    o.q_c.P.out_bf16 = p.qc; o.q_c.P.out_bf16_ld = d;
+    o.q_c.P.qnorm_w = W.qn_c; o.q_c.P.knorm_w = W.kn_c; o.q_c.P.n_q_end = d; o.q_c.P.n_k_end = d;
+    o.q_c.P.rope_T = T; o.q_c.P.use_rope = 0; o.q_c.P.eps = c.norm_eps;
+    o.kv_c = make_linear("cross.wkv", p.ymem, ML, d, W.wkv_c, 2 * d, 256, EPI_QKV);
+    o.kv_c.P.out_bf16 = p.kvc; o.kv_c.P.out_bf16_ld = 2 * d;
+    o.kv_c.P.qnorm_w = W.qn_c; o.kv_c.P.knorm_w = W.kn_c; o.kv_c.P.n_q_end = 0; o.kv_c.P.n_k_end = d;
+    o.kv_c.P.rope_T = L; o.kv_c.P.use_rope = 0; o.kv_c.P.eps = c.norm_eps;
+    o.wo_c = make_linear("cross.wo", p.att, M, d, W.wo_c, d, 256, EPI_AFFINE);
+    o.wo_c.P.res = p.h; o.wo_c.P.res_ld = d; o.wo_c.P.out_f32 = p.h; o.wo_c.P.out_f32_ld = d;
+    o.w13 = make_linear("ffn.w13", p.xn, M, d, W.w13, 2 * hid, 256, EPI_SWIGLU);
+    o.w13.P.out_bf16 = p.u; o.w13.P.out_bf16_ld = hid;
+    o.w2 = make_linear("ffn.w2", p.u, M, hid, W.w2, d, 256, EPI_AFFINE);
+    o.w2.P.gate = mod_l + 5 * d; o.w2.P.gate_ld = 6 * d; o.w2.P.gate_div = T;
+    o.w2.P.res = p.h; o.w2.P.res_ld = d; o.w2.P.out_f32 = p.h; o.w2.P.out_f32_ld = d;
+  }
+  p.g_out = make_linear("output", p.xn, M, d, e->w_out, c.out_channels, 256, EPI_AFFINE);
+
+  // algorithmic FLOPs of one evaluation (GEMMs + attention), for roofline reporting
+  double f = p.g_t13.flops + p.g_t2.flops + p.g_tb.flops + p.g_y13.flops + p.g_y2.flops + p.g_in.flops +
+             p.g_xe[0].flops + p.g_xe[1].flops + p.g_out.flops;
+  for (auto& o : p.lay)
+    f += o.qkv.flops + o.wo.flops + o.q_c.flops + o.kv_c.flops + o.wo_c.flops + o.w13.flops + o.w2.flops +
+         4.0 * Bc * (double)T * T * d + 4.0 * Bc * (double)T * L * d;
+  p.flops_per_eval = f;
+  e->dit = std::move(P);
+}
+
+// =====================================================================================================
+// DiT evaluation
+// =====================================================================================================
+template <int V>
+static void launch_rmsnorm(const float* x, const float* w, const float* shift, const float* scale, long long mod_ld,
+                           int rows_per_item, bf16* out, int M, float eps, cudaStream_t st) {
+  rmsnorm_mod_kernel<V><<<(M + 7) / 8, 256, 0, st>>>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps);
+}
+static void rmsnorm_mod(sab_engine* e, const float* x, const float* w, const float* shift, const float* scale,
+                        long long mod_ld, int rows_per_item, bf16* out, int M, cudaStream_t st) {
+  const int d = e->cfg.dim;
+  const float eps = e->cfg.norm_eps;
+  switch (d / 128) {
+#define SAB_RN(v) case v: launch_rmsnorm<v>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps, st); break;
+    SAB_RN(2) SAB_RN(4) SAB_RN(8) SAB_RN(12) SAB_RN(16) SAB_RN(20) SAB_RN(22) SAB_RN(24) SAB_RN(32)
+#undef SAB_RN
+    default: throw Error(fmt("rmsnorm: unsupported dim %d (add an instantiation)", d));
+  }
+  SAB_CUDA(cudaGetLastError());
+  count(e);
+}
+
+static void attention(sab_engine* e, const AttnParams& ap, int items, int heads, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SAB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
+  }
+  dim3 grid((ap.Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(ap);
+  SAB_CUDA(cudaGetLastError());
+  count(e);
+}
+
+static void gemm(sab_engine* e, const GemmOp& op, cudaStream_t st) {
+  launch_gemm(op, st);
+  count(e);
+}
+
+// final-layer variants: out = base + coef * velocity (ODE axpy fused in the output GEMM's epilogue)
+struct FinalSpec {
+  const float* base;   // nullptr: plain velocity
+  float coef;
+  float* out_f32;
+  bf16* out_bf16;      // next evaluation's GEMM operand (or nullptr)
+};
+
+static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, cudaStream_t st) {
+  DitPlan& p = *e->dit;
+  const sab_config& c = e->cfg;
+  const int d = c.dim, Bc = p.Bc, T = p.T, L = p.L, NL = c.n_layers, H = c.n_heads;
+  const int M = (int)p.M;
+  const float sl2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+
+  time_features_kernel<<<256, 256, 0, st>>>(time_dev, Bc, d, L, p.tfreq, p.mem_base, p.mem_in); count(e);
+  gemm(e, p.g_t13, st);
+  gemm(e, p.g_t2, st);
+  silu_cast_kernel<<<64, 256, 0, st>>>(p.t, p.t_silu, (long long)Bc * d); count(e);
+  gemm(e, p.g_tb, st);
+  build_mod_kernel<<<512, 256, 0, st>>>(e->tables, p.t0, p.mod, NL, Bc, d, e->final_table, p.t, p.fin); count(e);
+  gemm(e, p.g_y13, st);
+  gemm(e, p.g_y2, st);
+  gemm(e, p.g_in, st);
+  // x_embedder (patcher.py:138-164): GN(1) -> SiLU -> conv3, twice, + x
+  for (int b = 0; b < 2; ++b) {
+    const float* src = b == 0 ? p.x0 : p.c1;
+    gn_stats_kernel<<<dim3(GN_CHUNKS, Bc), 256, 0, st>>>(src, (long long)T * d, p.gn_partial); count(e);
+    gn_silu_kernel<<<dim3(64, Bc), 256, 0, st>>>(src, p.gn_partial, e->xe_gn_w[b], e->xe_gn_b[b], d, (long long)T * d,
+                                               1e-5f, p.gn_a);
+    count(e);
+    gemm(e, p.g_xe[b], st);
+  }
+  SAB_CUDA(cudaGetLastError());
+  for (int l = 0; l < NL; ++l) {
+    const LayerW& W = e->layers[l];
+    LayerOps& o = p.lay[l];
+    const float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
+    rmsnorm_mod(e, p.h, W.attn_norm, mod_l, mod_l + d, 6LL * d, T, p.xn, M, st);
+    gemm(e, o.qkv, st);
+    AttnParams a{};
+    a.q = p.qkv; a.q_ld = 3 * d; a.q_col0 = 0;
+    a.k = p.qkv; a.k_ld = 3 * d; a.k_col0 = d;
+    a.v = p.qkv; a.v_ld = 3 * d; a.v_col0 = 2 * d;
+    a.o = p.att; a.o_ld = d; a.key_mask = p.pad_mask; a.Tq = T; a.Tk = T; a.scale_log2 = sl2;
+    attention(e, a, Bc, H, st);
+    gemm(e, o.wo, st);
+    gemm(e, o.q_c, st);
+    gemm(e, o.kv_c, st);
+    AttnParams x{};
+    x.q = p.qc; x.q_ld = d; x.q_col0 = 0;
+    x.k = p.kvc; x.k_ld = 2 * d; x.k_col0 = 0;
+    x.v = p.kvc; x.v_ld = 2 * d; x.v_col0 = d;
+    x.o = p.att; x.o_ld = d; x.key_mask = p.text_mask; x.Tq = T; x.Tk = L; x.scale_log2 = sl2;
+    attention(e, x, Bc, H, st);
+    gemm(e, o.wo_c, st);
+    rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st);
+    gemm(e, o.w13, st);
+    gemm(e, o.w2, st);
+  }
+  rmsnorm_mod(e, p.h, e->final_norm, p.fin, p.fin + d, 2LL * d, T, p.xn, M, st);
+  GemmOp out = p.g_out;
+  out.P.res = fs.base; out.P.res_ld = 256; out.P.alpha = fs.coef;
+  out.P.out_f32 = fs.out_f32; out.P.out_f32_ld = 256;
+  out.P.out_bf16 = fs.out_bf16; out.P.out_bf16_ld = 256;
+  gemm(e, out, st);
+}
+
+// =====================================================================================================
+// codec plans
+// =====================================================================================================
+struct CodecStep {
+  enum Kind { GEMM, ENC0, DEC_LAST, LATENT_SPLIT } kind = GEMM;
+  GemmOp op;
+};
+struct CodecPlan {
+  int items = 0;       // waveforms per chunk
+  long long S = 0;     // samples per waveform
+  DevicePool pool;
+  std::vector<CodecStep> steps;
+  // end-point buffers
+  float* x_first = nullptr; bf16* a_first = nullptr;     // encoder stage 0
+  bf16* z_in = nullptr;                                  // decoder input [items, T, cz] bf16
+  bf16* a_last = nullptr;                                // decoder last-stage activated input
+  GemmOp* enc_out = nullptr;                             // in_proj (output pointer patched per chunk)
+  double flops = 0;
+};
+
+static int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  if (N % 96 == 0) return 96;
+  if (N % 64 == 0) return 64;
+  throw Error(fmt("codec: no GEMM tile for N=%d", N));
+}
+static int pick_bk(int cin) {
+  if (cin % 64 == 0) return 64;
+  if (cin % 32 == 0) return 32;
+  throw Error(fmt("codec: channel count %d not a multiple of 32", cin));
+}
+
+struct StageBufs { float* x; bf16* a; bf16* mid; };
+
+// Conv1d(c, c, k=7, dilation) 'same' + Snake  ->  Conv1d(c, c, 1) + residual  (+ Snake for the consumer)
+static void plan_resunit(CodecPlan& cp, const ResUnitW& R, int items, long long Tn, int C, const StageBufs& sb,
+                         const float* next_alpha, bool keep_x) {
+  const int bk = pick_bk(C), bn = pick_bn(C);
+  {
+    RunList rl;
+    for (int k = 0; k < 7; ++k) rl.add(0, (k - 3) * R.c7.dil, 0, C / bk);
+    CodecStep s;
+    s.op = make_gemm("codec.res.conv7", seq_view(sb.a, items, Tn, C), R.c7.w, C, bn, bk, EPI_AFFINE, rl);
+    s.op.P.bias = R.c7.bias;
+    s.op.P.out_act = sb.mid; s.op.P.out_act_ld = C; s.op.P.snake_alpha = R.a1;
+    cp.flops += s.op.flops;
+    cp.steps.push_back(s);
+  }
+  {
+    RunList rl;
+    rl.add(0, 0, 0, C / bk);
+    CodecStep s;
+    s.op = make_gemm("codec.res.conv1", seq_view(sb.mid, items, Tn, C), R.c1.w, C, bn, bk, EPI_AFFINE, rl);
+    s.op.P.bias = R.c1.bias;
+    s.op.P.res = sb.x; s.op.P.res_ld = C;
+    if (keep_x) { s.op.P.out_f32 = sb.x; s.op.P.out_f32_ld = C; }
+    s.op.P.out_act = sb.a; s.op.P.out_act_ld = C; s.op.P.snake_alpha = next_alpha;
+    cp.flops += s.op.flops;
+    cp.steps.push_back(s);
+  }
+}
+
+static CodecPlan* get_enc_plan(sab_engine* e, int items, long long S) {
+  auto key = std::make_pair(items, S);
+  auto it = e->enc_plans.find(key);
+  if (it != e->enc_plans.end()) return it->second.get();
+  const sab_config& c = e->cfg;
+  auto CP = std::make_unique<CodecPlan>();
+  CodecPlan& cp = *CP;
+  cp.items = items; cp.S = S;
+  int C = c.codec_encoder_dim;
+  long long Tn = S;
+  StageBufs sb{cp.pool.alloc<float>(items * Tn * C), cp.pool.alloc<bf16>(items * Tn * C), cp.pool.alloc<bf16>(items * Tn * C)};
+  cp.x_first = sb.x; cp.a_first = sb.a;
+  { CodecStep s; s.kind = CodecStep::ENC0; cp.steps.push_back(s); }
+  for (int i = 0; i < c.codec_n_rates; ++i) {
+    const EncBlockW& B = e->enc_blocks[i];
+    for (int j = 0; j < 3; ++j)
+      plan_resunit(cp, B.ru[j], items, Tn, C, sb, j < 2 ? B.ru[j + 1].a0 : B.a_down, j < 2);
+    // strided Conv1d(C, 2C, k=2s, stride s, pad s/2) over the [Tn/s, s*C] view of the activated stream
+    const int s = B.stride, pd = s / 2;
+    SAB_CHECK(Tn % s == 0, "encoder length %lld not divisible by rate %d", Tn, s);
+    const long long To = Tn / s;
+    const int C2 = 2 * C;
+    StageBufs nb{cp.pool.alloc<float>(items * To * C2), cp.pool.alloc<bf16>(items * To * C2),
+                 cp.pool.alloc<bf16>(items * To * C2)};
+    const int bk = 64;
+    SAB_CHECK((pd * C) % bk == 0, "encoder stride tap split not BK aligned");
+    RunList rl;
+    rl.add(0, -1, (s - pd) * C, pd * C / bk);
+    rl.add(0, 0, 0, s * C / bk);
+    rl.add(0, +1, 0, (s - pd) * C / bk);
+    CodecStep st;
+    AView av{sb.a, (int64_t)s * C, To, items, (int64_t)s * C, To * s * C};
+    st.op = make_gemm("codec.enc.down", av, B.down.w, C2, pick_bn(C2), bk, EPI_AFFINE, rl);
+    st.op.P.bias = B.down.bias;
+    const bool last = (i == c.codec_n_rates - 1);
+    st.op.P.out_f32 = nb.x; st.op.P.out_f32_ld = C2;
+    st.op.P.out_act = nb.a; st.op.P.out_act_ld = C2;
+    st.op.P.snake_alpha = last ? e->enc_final_alpha : e->enc_blocks[i + 1].ru[0].a0;
+    cp.flops += st.op.flops;
+    cp.steps.push_back(st);
+    sb = nb; C = C2; Tn = To;
+  }
+  {  // Snake (already applied) -> Conv1d(C, latent, k=3, pad 1) -> bf16 for in_proj
+    RunList rl;
+    for (int k = 0; k < 3; ++k) rl.add(0, k - 1, 0, C / 64);
+    bf16* zl = cp.pool.alloc<bf16>(items * Tn * c.codec_latent_dim);
+    CodecStep st;
+    st.op = make_gemm("codec.enc.final", seq_view(sb.a, items, Tn, C), e->enc_final.w, c.codec_latent_dim,
+                      pick_bn(c.codec_latent_dim), 64, EPI_AFFINE, rl);
+    st.op.P.bias = e->enc_final.bias;
+    st.op.P.out_bf16 = zl; st.op.P.out_bf16_ld = c.codec_latent_dim;
+    cp.flops += st.op.flops;
+    cp.steps.push_back(st);
+    RunList r1;
+    r1.add(0, 0, 0, c.codec_latent_dim / 64);
+    CodecStep s2;
+    s2.op = make_gemm("codec.in_proj", seq_view(zl, items, Tn, c.codec_latent_dim), e->in_proj.w,
+                      2 * c.codec_codebook_dim, pick_bn(2 * c.codec_codebook_dim), 64, EPI_AFFINE, r1);
+    s2.op.P.bias = e->in_proj.bias;
+    s2.op.P.out_f32_ld = 2 * c.codec_codebook_dim;  // out_f32 patched per call
+    cp.flops += s2.op.flops;
+    cp.steps.push_back(s2);
+  }
+  cp.enc_out = &cp.steps.back().op;
+  CodecPlan* r = CP.get();
+  e->enc_plans[key] = std::move(CP);
+  return r;
+}
+
+static CodecPlan* get_dec_plan(sab_engine* e, int items, long long T) {
+  auto key = std::make_pair(items, T);
+  auto it = e->dec_plans.find(key);
+  if (it != e->dec_plans.end()) return it->second.get();
+  const sab_config& c = e->cfg;
+  auto CP = std::make_unique<CodecPlan>();
+  CodecPlan& cp = *CP;
+  cp.items = items;
+  const int cz = c.codec_codebook_dim, ld = c.codec_latent_dim;
+  long long Tn = T;
+  cp.z_in = cp.pool.alloc<bf16>(items * Tn * cz);
+  { CodecStep s; s.kind = CodecStep::LATENT_SPLIT; cp.steps.push_back(s); }
+  bf16* e0 = cp.pool.alloc<bf16>(items * Tn * ld);
+  {
+    RunList rl;
+    rl.add(0, 0, 0, cz / 64);
+    CodecStep s;
+    s.op = make_gemm("codec.out_proj", seq_view(cp.z_in, items, Tn, cz), e->out_proj.w, ld, pick_bn(ld), 64, EPI_AFFINE, rl);
+    s.op.P.bias = e->out_proj.bias;
+    s.op.P.out_bf16 = e0; s.op.P.out_bf16_ld = ld;
+    cp.flops += s.op.flops;
+    cp.steps.push_back(s);
+  }
+  int C = c.codec_decoder_dim;
+  bf16* a_cur = cp.pool.alloc<bf16>(items * Tn * C);
+  {
+    RunList rl;
+    for (int k = 0; k < 7; ++k) rl.add(0, k - 3, 0, ld / 64);
+    CodecStep s;
+    s.op = make_gemm("codec.dec.conv_in", seq_view(e0, items, Tn, ld), e->dec0.w, C, pick_bn(C), 64, EPI_AFFINE, rl);
+    s.op.P.bias = e->dec0.bias;
+    s.op.P.out_act = a_cur; s.op.P.out_act_ld = C; s.op.P.snake_alpha = e->dec_blocks[0].a_up;
+    cp.flops += s.op.flops;
+    cp.steps.push_back(s);
+  }
+  for (int i = 0; i < c.codec_n_rates; ++i) {
+    const DecBlockW& B = e->dec_blocks[i];
+    const int s = B.stride, Co = B.cout;
+    const long long To = Tn * s;
+    StageBufs sb{cp.pool.alloc<float>(items * To * Co), cp.pool.alloc<bf16>(items * To * Co),
+                 cp.pool.alloc<bf16>(items * To * Co)};
+    {
+      // ConvTranspose1d(C, Co, k=2s, stride s, pad s/2): output rows viewed as [Tn, s*Co]
+      const int bk = pick_bk(C);
+      int bn = pick_bn(Co);                       // must divide the tap switch (s/2)*Co and the period s*Co
+      while (bn > 64 && (((s / 2) * Co) % bn != 0)) bn = (bn == 256) ? 192 : (bn == 192) ? 128 : (bn == 128) ? 96 : 64;
+      RunList rl;
+      rl.period = s * Co; rl.sw = (s / 2) * Co;
+      rl.add(0, 0, 0, C / bk); rl.add(0, -1, 0, C / bk);
+      rl.add(1, 0, 0, C / bk); rl.add(1, +1, 0, C / bk);
+      CodecStep st;
+      st.op = make_gemm("codec.dec.up", seq_view(a_cur, items, Tn, C), B.up.w, s * Co, bn, bk, EPI_AFFINE, rl);
+      st.op.P.bias = B.up.bias; st.op.P.bias_mod = Co;
+      st.op.P.out_f32 = sb.x; st.op.P.out_f32_ld = (long long)s * Co;
+      st.op.P.out_act = sb.a; st.op.P.out_act_ld = (long long)s * Co; st.op.P.snake_alpha = B.ru[0].a0;
+      cp.flops += st.op.flops;
+      cp.steps.push_back(st);
+    }
+    const bool last = (i == c.codec_n_rates - 1);
+    const float* after = last ? e->dec_final_alpha : e->dec_blocks[i + 1].a_up;
+    for (int j = 0; j < 3; ++j) plan_resunit(cp, B.ru[j], items, To, Co, sb, j < 2 ? B.ru[j + 1].a0 : after, j < 2);
+    a_cur = sb.a; C = Co; Tn = To;
+  }
+  cp.a_last = a_cur;
+  cp.S = Tn;
+  { CodecStep s; s.kind = CodecStep::DEC_LAST; cp.steps.push_back(s); }
+  cp.flops += 2.0 * items * (double)Tn * C * 7;
+  CodecPlan* r = CP.get();
+  e->dec_plans[key] = std::move(CP);
+  return r;
+}
+
+sab_engine::~sab_engine() {
+  dit.reset();
+  enc_plans.clear();
+  dec_plans.clear();
+  if (staging) cudaFree(staging);
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define SAB_API_BEGIN try {
+#define SAB_API_END                                   \
+  }                                                   \
+  catch (const std::exception& ex) {                  \
+    g_last_error = ex.what();                         \
+    return 1;                                         \
+  }                                                   \
+  return 0;
+
+extern "C" {
+
+const char* sab_last_error(void) { return g_last_error.c_str(); }
+int sab_version(void) { return 1; }
+
+int sab_create(const sab_config* cfg, int device, sab_engine** out) {
+  SAB_API_BEGIN
+  SAB_CHECK(cfg && out, "null argument");
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  SAB_CHECK(ce == cudaSuccess && n_dev > 0, "no CUDA device: the SAM-Audio B200 path has no CPU fallback (%s)",
+            cudaGetErrorString(ce));
+  SAB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SAB_CUDA(cudaGetDeviceProperties(&prop, device));
+  SAB_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  SAB_CHECK(cfg->dim % 128 == 0 && cfg->dim / cfg->n_heads == 128, "dim must be n_heads*128");
+  SAB_CHECK(cfg->ffn_hidden % 64 == 0, "ffn_hidden must be a multiple of 64");
+  SAB_CHECK(cfg->codec_n_rates >= 1 && cfg->codec_n_rates <= 8, "bad codec_n_rates");
+  auto* e = new sab_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  try {
+    register_weights(e);
+    e->rope_len = cfg->max_positions;
+    e->rope = reinterpret_cast<float2*>(e->wpool.alloc<float>((int64_t)e->rope_len * 64 * 2));
+    rope_table_kernel<<<(e->rope_len * 64 + 255) / 256, 256>>>(e->rope, e->rope_len, 128, cfg->rope_theta);
+    SAB_CUDA(cudaGetLastError());
+    SAB_CUDA(cudaDeviceSynchronize());
+  } catch (...) {
+    delete e;
+    throw;
+  }
+  *out = e;
+  SAB_API_END
+}
+
+int sab_destroy(sab_engine* e) {
+  SAB_API_BEGIN
+  if (e) {
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    delete e;
+  }
+  SAB_API_END
+}
+
+int sab_load_weight(sab_engine* e, const char* name, const float* data, const int64_t* shape, int ndim, int is_device,
+                    void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && name && data, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto it = e->slots.find(name);
+  SAB_CHECK(it != e->slots.end(), "unexpected weight '%s'", name);
+  Slot& s = it->second;
+  int64_t n = 1, n_expected = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  for (auto v : s.shape) n_expected *= v;
+  std::vector<int64_t> sq_a, sq_b;  // compare with singleton dims squeezed ([1,C,1] alpha == [C])
+  for (auto v : s.shape) if (v != 1) sq_a.push_back(v);
+  for (int i = 0; i < ndim; ++i) if (shape[i] != 1) sq_b.push_back(shape[i]);
+  SAB_CHECK(sq_a == sq_b, "weight '%s': shape mismatch (expected %lld elements, got %lld)", name,
+            (long long)n_expected, (long long)n);
+  const float* src = data;
+  if (!is_device) {
+    if (e->staging_elems < n) {
+      if (e->staging) { SAB_CUDA(cudaStreamSynchronize(st)); SAB_CUDA(cudaFree(e->staging)); }
+      SAB_CUDA(cudaMalloc(&e->staging, n * sizeof(float)));
+      e->staging_elems = n;
+    }
+    SAB_CUDA(cudaMemcpyAsync(e->staging, data, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    src = e->staging;
+  }
+  s.load(src, st);
+  if (!is_device) SAB_CUDA(cudaStreamSynchronize(st));  // staging buffer is reused by the next call
+  s.loaded = true;
+  e->finalized = false;
+  SAB_API_END
+}
+
+int sab_finalize_weights(sab_engine* e, void* stream) {
+  SAB_API_BEGIN
+  cudaStream_t st = (cudaStream_t)stream;
+  std::string missing;
+  int n_missing = 0;
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) { if (n_missing++ < 8) missing += kv.first + " "; }
+  SAB_CHECK(n_missing == 0, "Missing keys (%d): %s", n_missing, missing.c_str());
+  const int d = e->cfg.dim;
+  // constant video term for text-only prompts: LayerNorm(conv bias)   
+  ln_vector_kernel<<<1, 256, 0, st>>>(e->vid_b, e->vid_ln_w, e->vid_ln_b, d, e->vid_const);
+  // anchor table: embed [n,128] @ proj^T [128,d]
+  const int n = e->cfg.n_anchor_tokens;
+  small_abt_kernel<<<(n * d + 255) / 256, 256, 0, st>>>(e->anchor_embed, e->anchor_proj, e->anchor_table, n, d,
+                                                         e->cfg.anchor_dim);
+  SAB_CUDA(cudaGetLastError());
+  SAB_CUDA(cudaStreamSynchronize(st));
+  e->finalized = true;
+  SAB_API_END
+}
+
+int sab_prepare(sab_engine* e, int Bc, int T, int L, const float* features, const float* text_features,
+                const uint8_t* text_mask, const float* video_features, const int64_t* anchor_ids, int n_ids,
+                const int64_t* anchor_alignment, const uint8_t* audio_pad_mask, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && e->finalized, "weights not finalized");
+  SAB_CHECK(Bc > 0 && T > 0 && L > 0, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!e->dit || e->dit->Bc != Bc || e->dit->T != T || e->dit->L != L) {
+    SAB_CUDA(cudaStreamSynchronize(st));
+    e->dit.reset();
+    build_dit_plan(e, Bc, T, L);
+  }
+  DitPlan& p = *e->dit;
+  const sab_config& c = e->cfg;
+  const int d = c.dim;
+  SAB_CHECK(n_ids <= p.n_ids_cap, "too many anchors per clip (%d)", n_ids);
+  const long long M = p.M, ML = p.ML;
+  SAB_CUDA(cudaMemcpyAsync(p.pad_mask, audio_pad_mask, M, cudaMemcpyDeviceToDevice, st));
+  SAB_CUDA(cudaMemcpyAsync(p.text_mask, text_mask, ML, cudaMemcpyDeviceToDevice, st));
+  SAB_CUDA(cudaMemcpyAsync(p.anchor_ids, anchor_ids, (size_t)Bc * n_ids * 8, cudaMemcpyDeviceToDevice, st));
+  SAB_CUDA(cudaMemcpyAsync(p.anchor_align, anchor_alignment, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+  cast_bf16_kernel<<<512, 256, 0, st>>>(features, p.feat_bf, M * 256); count(e);
+  cast_bf16_kernel<<<64, 256, 0, st>>>(text_features, p.text_bf, ML * c.text_dim); count(e);
+  gemm(e, p.g_cond, st);
+  gemm(e, p.g_mem, st);
+  const float* vproj = nullptr;
+  if (video_features) {
+    transpose_cast_kernel<<<1024, 256, 0, st>>>(video_features, c.vision_dim, T, M * c.vision_dim, p.vid_bf); count(e);
+    gemm(e, p.g_vid, st);
+    vproj = p.vproj;
+  }
+  cond_finish_kernel<<<(int)((M + 7) / 8), 256, 0, st>>>(p.cond, (int)M, d, T, vproj, e->vid_ln_w, e->vid_ln_b, e->vid_const,
+                                                        e->vid_gate, e->anchor_table,
+                                                        reinterpret_cast<const long long*>(p.anchor_ids), n_ids,
+                                                        reinterpret_cast<const long long*>(p.anchor_align), e->anchor_gate);
+  count(e);
+  SAB_CUDA(cudaGetLastError());
+  SAB_API_END
+}
+
+int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float* velocity, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && e->dit, "sab_prepare must be called first");
+  cudaStream_t st = (cudaStream_t)stream;
+  DitPlan& p = *e->dit;
+  cast_bf16_kernel<<<512, 256, 0, st>>>(noisy, p.y_bf, p.M * 256); count(e);
+  FinalSpec fs{nullptr, 1.f, velocity, nullptr};
+  dit_eval(e, time, fs, st);
+  SAB_API_END
+}
+
+int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && e->dit, "sab_prepare must be called first");
+  SAB_CHECK(n_steps >= 1 && 2 * n_steps <= 64, "n_steps out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  DitPlan& p = *e->dit;
+  const long long n = p.M * 256;
+  // evaluation times k/n and (k + 1/2)/n, broadcast over the batch (model.py:280 t.expand)
+  std::vector<float> times((size_t)2 * n_steps * p.Bc);
+  for (int k = 0; k < n_steps; ++k)
+    for (int b = 0; b < p.Bc; ++b) {
+      times[(size_t)(2 * k) * p.Bc + b] = (float)k / (float)n_steps;
+      times[(size_t)(2 * k + 1) * p.Bc + b] = ((float)k + 0.5f) / (float)n_steps;
+    }
+  SAB_CUDA(cudaMemcpyAsync(p.time_dev, times.data(), times.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  SAB_CUDA(cudaStreamSynchronize(st));  // `times` is a stack-owned host buffer
+  SAB_CUDA(cudaMemcpyAsync(p.y, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  cast_bf16_kernel<<<512, 256, 0, st>>>(p.y, p.y_bf, n); count(e);
+  const float dt = 1.0f / (float)n_steps;
+  for (int k = 0; k < n_steps; ++k) {
+    // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)
+    FinalSpec a{p.y, 0.5f * dt, p.ymid, p.y_bf};
+    dit_eval(e, p.time_dev + (size_t)(2 * k) * p.Bc, a, st);
+    FinalSpec b{p.y, dt, p.y, p.y_bf};
+    dit_eval(e, p.time_dev + (size_t)(2 * k + 1) * p.Bc, b, st);
+  }
+  SAB_CUDA(cudaMemcpyAsync(latent, p.y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAB_API_END
+}
+
+static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_in, const float* latent_in, int T,
+                      float* out, cudaStream_t st) {
+  const sab_config& c = e->cfg;
+  for (auto& s : cp.steps) {
+    switch (s.kind) {
+      case CodecStep::ENC0: {
+        const int C0 = c.codec_encoder_dim;
+        const long long n = cp.S * (C0 / 4);
+        enc_conv0_kernel<<<dim3((unsigned)((n + 255) / 256), items), 256, 0, st>>>(
+            wav_in, cp.S, C0, e->enc0_w, e->enc0_b, e->enc_blocks[0].ru[0].a0, cp.x_first, cp.a_first);
+        count(e);
+        break;
+      }
+      case CodecStep::LATENT_SPLIT: {
+        const int cz = c.codec_codebook_dim;
+        latent_split_kernel<<<512, 256, 0, st>>>(latent_in, T, cz, (long long)items * T * cz, cp.z_in);
+        count(e);
+        break;
+      }
+      case CodecStep::DEC_LAST: {
+        const int C = c.codec_decoder_dim >> c.codec_n_rates;
+        const int smem = ((DEC_LAST_TB + 6) * (C + 2) + 2) * 2 + 7 * C * 4;
+        dec_last_kernel<<<dim3((unsigned)((cp.S + DEC_LAST_TB - 1) / DEC_LAST_TB), items), DEC_LAST_TB, smem, st>>>(
+            cp.a_last, cp.S, C, e->dec_last_w, e->dec_last_b, out);
+        count(e);
+        break;
+      }
+      default: {
+        GemmOp op = s.op;
+        op.P.n_items = items;
+        if (&s.op == cp.enc_out) op.P.out_f32 = out;
+        const long long tiles = (long long)items * op.P.tiles_per_item * op.P.n_tiles_n;
+        op.grid = (int)std::min<long long>(tiles, g_sm_count);
+        gemm(e, op, st);
+      }
+    }
+  }
+  SAB_CUDA(cudaGetLastError());
+}
+
+static int codec_chunk(const sab_engine* e, long long S_samples, bool decoder) {
+  // fp32 stream + two bf16 operand buffers per stage (8 B per activation element): ~0.56 GB per 10 s clip in the
+  // encoder, ~0.85 GB per 10 s waveform in the decoder; keep a chunk's workspace near 12 GB
+  (void)e;
+  const double per_item = (double)S_samples / 480000.0 * (decoder ? 0.85e9 : 0.56e9);
+  int n = (int)(12e9 / per_item);
+  return n < 1 ? 1 : (n > 64 ? 64 : n);
+}
+
+int sab_encode(sab_engine* e, const float* wav, int B, int64_t S, float* features, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && e->finalized, "weights not finalized");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long hop = 1;
+  for (int i = 0; i < e->cfg.codec_n_rates; ++i) hop *= e->cfg.codec_encoder_rates[i];
+  SAB_CHECK(S % hop == 0, "S=%lld must be padded to a multiple of hop=%lld (codec.py:72-78)", (long long)S, hop);
+  const long long T = S / hop;
+  const int chunk = std::min(B, codec_chunk(e, S, false));
+  CodecPlan* cp = get_enc_plan(e, chunk, S);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = std::min(chunk, B - b0);
+    run_codec(e, *cp, n, wav + (long long)b0 * S, nullptr, (int)T,
+              features + (long long)b0 * T * 2 * e->cfg.codec_codebook_dim, st);
+  }
+  SAB_API_END
+}
+
+int sab_decode(sab_engine* e, const float* latent, int Bc, int T, float* wav, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && e->finalized, "weights not finalized");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long hop = 1;
+  for (int i = 0; i < e->cfg.codec_n_rates; ++i) hop *= e->cfg.codec_decoder_rates[i];
+  const long long S = (long long)T * hop;
+  const int items = 2 * Bc;
+  int chunk = std::min(items, codec_chunk(e, S, true));
+  if (chunk > 1) chunk &= ~1;  // whole clips per chunk
+  CodecPlan* cp = get_dec_plan(e, chunk, T);
+  const int cz = e->cfg.codec_codebook_dim;
+  for (int i0 = 0; i0 < items; i0 += chunk) {
+    const int n = std::min(chunk, items - i0);
+    // items (2b, 2b+1) live in latent row b: chunk boundaries are clip boundaries
+    run_codec(e, *cp, n, nullptr, latent + (long long)(i0 / 2) * T * 2 * cz, T, wav + (long long)i0 * S, st);
+  }
+  SAB_API_END
+}
+
+int64_t sab_launch_count(sab_engine* e, int reset) {
+  if (!e) return -1;
+  const int64_t v = e->launches;
+  if (reset) e->launches = 0;
+  return v;
+}
+
+int64_t sab_workspace_bytes(sab_engine* e) {
+  if (!e) return -1;
+  int64_t b = e->wpool.bytes;
+  if (e->dit) b += e->dit->pool.bytes;
+  for (auto& kv : e->enc_plans) b += kv.second->pool.bytes;
+  for (auto& kv : e->dec_plans) b += kv.second->pool.bytes;
+  return b;
+}
+
+// ---- test seams ----
+int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk, void* stream) {
+  SAB_API_BEGIN
+  if (!g_sm_count) {
+    cudaDeviceProp prop;
+    SAB_CUDA(cudaGetDeviceProperties(&prop, 0));
+    g_sm_count = prop.multiProcessorCount;
+  }
+  RunList rl;
+  SAB_CHECK(K % bk == 0, "K must be a multiple of bk");
+  rl.add(0, 0, 0, K / bk);
+  GemmOp op = make_gemm("test", flat_view((const bf16*)a_bf16, M, K), (const bf16*)b_bf16, N, bn, bk, EPI_AFFINE, rl);
+  op.P.out_f32 = c; op.P.out_f32_ld = N;
+  launch_gemm(op, (cudaStream_t)stream);
+  SAB_API_END
+}
+
+int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, const void* k, const void* v,
+                       const uint8_t* key_mask, void* o, void* stream) {
+  SAB_API_BEGIN
+  SAB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  AttnParams a{};
+  const long long ld = (long long)heads * 128;
+  a.q = (const bf16*)q; a.q_ld = ld; a.k = (const bf16*)k; a.k_ld = ld; a.v = (const bf16*)v; a.v_ld = ld;
+  a.o = (bf16*)o; a.o_ld = ld; a.key_mask = key_mask; a.Tq = Tq; a.Tk = Tk;
+  a.scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+  dim3 grid((Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(a);
+  SAB_CUDA(cudaGetLastError());
+  SAB_API_END
+}
+
+}  // extern "C"

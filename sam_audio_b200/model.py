@@ -1,0 +1,263 @@
+"""SAMAudio — B200 drop-in for the reference's ``model.separate()`` path.
+
+Same public surface as the reference class (reference: sam_audio/model/model.py:75-359,
+sam_audio/model/base.py:17-62): ``SAMAudio.from_pretrained``, ``.eval()/.to()/.cuda()``,
+``.sample_rate``, ``.separate(batch, noise=None, ode_opt=DFLT_ODE_OPT,
+reranking_candidates=1, predict_spans=False) -> SeparationResult``, ``.forward`` (one ODE
+function evaluation), ``.unbatch``.  All arithmetic of the path runs in
+libsamaudio_b200.so (hand-written sm_100a kernels) through the C ABI in
+include/samaudio_b200.h; this file only moves pointers and mirrors control flow.
+There is no PyTorch / CPU fallback: without the library and a B200 it raises.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _capi
+from .config import SAMAudioConfig
+from .processor import Batch
+from .text_encoder import SyntheticTextEncoder, T5TextEncoder
+
+DFLT_ODE_OPT = {"method": "midpoint", "options": {"step_size": 2 / 32}}
+
+_SKIP_PREFIXES = re.compile(r"^(text_encoder|visual_ranker|text_ranker|span_predictor|vision_encoder)\.")
+
+
+@dataclass
+class SeparationResult:
+    target: List[torch.Tensor]
+    residual: List[torch.Tensor]
+    noise: torch.Tensor
+
+
+def fold_weight_norm(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """w = g * v / ||v||  (norm over all dims but 0), for both torch weight-norm spellings
+    (``weight_g/weight_v`` and ``parametrizations.weight.original0/1``)."""
+    out: Dict[str, torch.Tensor] = {}
+    pending: Dict[str, Dict[str, torch.Tensor]] = {}
+    for k, v in state_dict.items():
+        m = re.match(r"^(.*)\.(weight_g|weight_v|parametrizations\.weight\.original[01])$", k)
+        if not m:
+            out[k] = v
+            continue
+        kind = "g" if m.group(2) in ("weight_g", "parametrizations.weight.original0") else "v"
+        pending.setdefault(m.group(1), {})[kind] = v
+    for base, gv in pending.items():
+        g, v = gv["g"].float(), gv["v"].float()
+        norm = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+        out[f"{base}.weight"] = g * v / norm
+    return out
+
+
+class SAMAudio(torch.nn.Module):
+    config_cls = SAMAudioConfig
+    revision = None
+
+    def __init__(self, cfg: SAMAudioConfig, text_encoder: Optional[torch.nn.Module] = None,
+                 allow_random_text_encoder: bool = False):
+        super().__init__()
+        cfg.transformer.check_supported()
+        self.cfg = cfg
+        if text_encoder is None:
+            text_encoder = T5TextEncoder(cfg.text_encoder, allow_random_init=allow_random_text_encoder)
+        self.text_encoder = text_encoder
+        self.vision_encoder = None      # PE-Core-L14 (third party) — SURVEY §8f-2 "next" row
+        self.visual_ranker = None       # rerankers are outside the hot path (default config: None)
+        self.text_ranker = None
+        self._engine: Optional[_capi.Engine] = None
+        self._state: Optional[Dict[str, torch.Tensor]] = None
+        self._device = torch.device("cpu")
+        self.register_buffer("_anchor", torch.zeros(1), persistent=False)
+
+    # ------------------------------------------------------------------ loading
+    @classmethod
+    def from_pretrained(cls, model_id: str, map_location: str = "cpu", strict: bool = True, **model_kwargs):
+        if os.path.isdir(model_id):
+            root = model_id
+        else:
+            from huggingface_hub import snapshot_download
+            root = snapshot_download(repo_id=model_id, revision=cls.revision)
+        with open(os.path.join(root, "config.json")) as f:
+            config = json.load(f)
+        ctor_kwargs = {}
+        for k, v in model_kwargs.items():
+            if k in config:
+                config[k] = v
+            else:
+                ctor_kwargs[k] = v
+        model = cls(cls.config_cls(**config), **ctor_kwargs)
+        sd = torch.load(os.path.join(root, "checkpoint.pt"), weights_only=True, map_location=map_location)
+        model.load_state_dict(sd, strict=strict)
+        return model
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Same tolerance as the reference (model.py:346-359): encoder / ranker / span-predictor keys are
+        loaded elsewhere; everything else must match exactly (checked by the engine)."""
+        sd = {k: v for k, v in state_dict.items() if not _SKIP_PREFIXES.match(k)}
+        self._state = fold_weight_norm(sd)
+        if self._engine is not None:
+            self._push_weights()
+
+    def _push_weights(self):
+        assert self._engine is not None and self._state is not None
+        try:
+            for k, v in self._state.items():
+                self._engine.load_weight(k, v)
+            self._engine.finalize()
+        except RuntimeError as exc:
+            raise RuntimeError(f"load_state_dict: {exc}") from exc
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        dev = self._anchor.device
+        if dev != self._device:
+            self._device = dev
+            if self._engine is not None:
+                self._engine.close()
+                self._engine = None
+        return r
+
+    def _ensure_engine(self) -> _capi.Engine:
+        if self._engine is None:
+            if self._device.type != "cuda":
+                raise RuntimeError("sam_audio_b200.SAMAudio runs on a B200 only: call .cuda() first "
+                                   "(there is no CPU path)")
+            if self._state is None:
+                raise RuntimeError("no weights loaded: call load_state_dict()/from_pretrained() first")
+            idx = self._device.index if self._device.index is not None else torch.cuda.current_device()
+            with torch.cuda.device(idx):
+                self._engine = _capi.Engine(self.cfg, idx)
+                self._push_weights()
+        return self._engine
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def sample_rate(self) -> int:
+        return self.cfg.audio_codec.sample_rate
+
+    def device(self):
+        return self._anchor.device
+
+    # ------------------------------------------------------------------ pieces of separate()
+    def _pad(self, wavs: torch.Tensor) -> torch.Tensor:
+        hop = self.cfg.audio_codec.hop_length
+        n = wavs.size(-1)
+        if n % hop:
+            return F.pad(wavs, (0, hop - n % hop), "reflect")   # codec.py:72-78
+        return wavs
+
+    def _get_audio_features(self, audios: torch.Tensor) -> torch.Tensor:
+        eng = self._ensure_engine()
+        wav = self._pad(audios.float()).squeeze(1).contiguous()
+        B, S = wav.shape
+        T = S // self.cfg.audio_codec.hop_length
+        feats = torch.empty(B, T, 2 * self.cfg.audio_codec.codebook_dim, device=wav.device, dtype=torch.float32)
+        eng.encode(wav, feats)
+        return feats
+
+    @staticmethod
+    def _repeat(t: Optional[torch.Tensor], c: int):
+        if t is None or c == 1:
+            return t
+        return t.repeat_interleave(c, dim=0)
+
+    def _install_conditioning(self, audio_features, text_features, text_mask, masked_video_features,
+                              anchor_ids, anchor_alignment, audio_pad_mask):
+        eng = self._ensure_engine()
+        Bc, T, _ = audio_features.shape
+        L = text_features.shape[1]
+        if audio_pad_mask is None:
+            audio_pad_mask = torch.ones(Bc, T, dtype=torch.bool, device=audio_features.device)
+        if text_mask is None:
+            text_mask = torch.ones(Bc, L, dtype=torch.bool, device=audio_features.device)
+        vid = None if masked_video_features is None else masked_video_features.float().contiguous()
+        eng.prepare(Bc, T, L, audio_features.float().contiguous(), text_features.float().contiguous(),
+                    text_mask.to(torch.uint8).contiguous(), vid, anchor_ids.long().contiguous(),
+                    anchor_alignment.long().contiguous(), audio_pad_mask.to(torch.uint8).contiguous())
+
+    @torch.inference_mode()
+    def forward(self, noisy_audio, audio_features, text_features, time, masked_video_features=None,
+                text_mask=None, anchor_ids=None, anchor_alignment=None, audio_pad_mask=None):
+        """One ODE function evaluation (reference model.py:130-180)."""
+        eng = self._ensure_engine()
+        Bc, T, _ = audio_features.shape
+        if anchor_ids is None:
+            anchor_ids = torch.tensor([[0, 3]], device=noisy_audio.device).repeat(Bc, 1)
+            anchor_alignment = torch.zeros(Bc, T, dtype=torch.long, device=noisy_audio.device)
+        self._install_conditioning(audio_features, text_features, text_mask, masked_video_features,
+                                   anchor_ids, anchor_alignment, audio_pad_mask)
+        out = torch.empty_like(noisy_audio, dtype=torch.float32)
+        eng.dit_forward(noisy_audio.float().contiguous(), time.float().contiguous(), out)
+        return out
+
+    @torch.inference_mode()
+    def separate(self, batch: Batch, noise: Optional[torch.Tensor] = None, ode_opt: Dict[str, Any] = DFLT_ODE_OPT,
+                 reranking_candidates: int = 1, predict_spans: bool = False) -> SeparationResult:
+        eng = self._ensure_engine()
+        c = int(reranking_candidates)
+        if ode_opt.get("method", "midpoint") != "midpoint":
+            raise NotImplementedError("only the reference's midpoint solver is implemented")
+        n_steps = round(1.0 / float(ode_opt.get("options", {}).get("step_size", 2 / 32)))
+
+        feats = self._get_audio_features(batch.audios)                      # [B, T, 256]
+        text_features, text_mask = self.text_encoder(batch.descriptions)
+        B, T, C2 = feats.shape
+        video = None
+        if batch.masked_video is not None:
+            if self.vision_encoder is None:
+                raise NotImplementedError("visual prompting needs the PE-Core vision encoder "
+                                          "(third-party; SURVEY §8f-2) — attach one as model.vision_encoder")
+            video = self.vision_encoder(batch.masked_video).transpose(1, 2)
+        # reference behaviour: conditioning is fixed before span prediction; the
+        # span predictor (PE-A-Frame, third party) only mutates `batch`.
+        if predict_spans and hasattr(self, "span_predictor") and batch.anchors is None:
+            batch = self.predict_spans(batch, feats, batch.audio_pad_mask)  # pragma: no cover
+        self._install_conditioning(self._repeat(feats, c), self._repeat(text_features, c),
+                                   self._repeat(text_mask, c), self._repeat(video, c),
+                                   self._repeat(batch.anchor_ids, c), self._repeat(batch.anchor_alignment, c),
+                                   self._repeat(batch.audio_pad_mask, c))
+        if noise is None:
+            noise = torch.randn(B * c, T, C2, device=feats.device, dtype=torch.float32)
+        noise = noise.to(device=feats.device, dtype=torch.float32).contiguous()
+        latent = torch.empty_like(noise)
+        eng.solve(noise, n_steps, latent)
+
+        hop = self.cfg.audio_codec.hop_length
+        wavs = torch.empty(B * c, 2, T * hop, device=feats.device, dtype=torch.float32)
+        eng.decode(latent, B * c, T, wavs)
+
+        sizes = (batch.sizes * hop).int()                                   # codec.py:91-97
+        tgt = self.unbatch(wavs[:, 0].view(B, c, -1), sizes)
+        res = self.unbatch(wavs[:, 1].view(B, c, -1), sizes)
+        if c > 1 and (self.visual_ranker is not None or self.text_ranker is not None):
+            raise NotImplementedError("rerankers (CLAP / ImageBind / Judge) are outside the B200 hot path")
+        idxs = [0] * B                                                      # model.py:329-330
+        return SeparationResult(target=[w[i] for w, i in zip(tgt, idxs)],
+                                residual=[w[i] for w, i in zip(res, idxs)], noise=noise)
+
+    def unbatch(self, wavs: torch.Tensor, sizes: torch.Tensor, time_dim: int = -1):
+        return [row.narrow(dim=time_dim, start=0, length=int(n)) for row, n in zip(wavs, sizes)]
+
+    # ------------------------------------------------------------------ introspection
+    def launch_count(self, reset: bool = False) -> int:
+        return self._ensure_engine().launch_count(reset)
+
+
+def build_synthetic_model(name: str = "sam-audio-tiny", seed: int = 0, text: str = "synthetic",
+                          device: str = "cuda", weights_device: str = "cpu") -> SAMAudio:
+    """Random-init model of a stand-in shape (no checkpoints in the sandbox)."""
+    from .config import stand_in_config
+    from .synthetic import make_state_dict
+    cfg = stand_in_config(name)
+    te = SyntheticTextEncoder(cfg.text_encoder.dim) if text == "synthetic" else \
+        T5TextEncoder(cfg.text_encoder, allow_random_init=True)
+    m = SAMAudio(cfg, text_encoder=te)
+    m.load_state_dict(make_state_dict(cfg, seed=seed, device=weights_device))
+    return m.eval().to(device)
