@@ -101,6 +101,11 @@ int sab_decode(sab_engine* e, const float* latent, int Bc, int T, float* wav, vo
 int64_t sab_launch_count(sab_engine* e, int reset);
 /* Workspace bytes currently held. */
 int64_t sab_workspace_bytes(sab_engine* e);
+/* Live per-kernel timing for roofline reporting: with profiling on, one CUDA event is recorded in front of
+ * every launch on `stream`; sab_profile_report aggregates the inter-event times per kernel tag as JSON
+ * ({"tag": {"launches","ms","flops","bytes"}}) and clears the log. */
+int sab_profile(sab_engine* e, int enable, void* stream);
+int sab_profile_report(sab_engine* e, char* json_out, int64_t capacity, void* stream);
 
 /* ---- unit-test seams (used by tests/ only; stable but not part of the drop-in surface) ---- */
 /* C[M,N] (fp32) = A[M,K] (bf16) * B[N,K]^T (bf16) through the tcgen05 GEMM (BN = 128 or 256, BK = 64 or 32). */

@@ -33,7 +33,7 @@ class SabConfig(ctypes.Structure):
 EXPORTS = [
     "sab_last_error", "sab_version", "sab_create", "sab_destroy", "sab_load_weight", "sab_finalize_weights",
     "sab_encode", "sab_prepare", "sab_dit_forward", "sab_solve", "sab_decode", "sab_launch_count",
-    "sab_workspace_bytes", "sab_test_gemm", "sab_test_attention",
+    "sab_workspace_bytes", "sab_profile", "sab_profile_report", "sab_test_gemm", "sab_test_attention",
 ]
 
 
@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         L.sab_launch_count.restype = i64
         L.sab_workspace_bytes.argtypes = [vp]
         L.sab_workspace_bytes.restype = i64
+        L.sab_profile.argtypes = [vp, i32, vp]
+        L.sab_profile_report.argtypes = [vp, ctypes.c_char_p, i64, vp]
         L.sab_test_gemm.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, vp]
         L.sab_test_attention.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         _lib = L
@@ -155,6 +157,15 @@ class Engine:
 
     def launch_count(self, reset=False) -> int:
         return int(lib().sab_launch_count(self._h, 1 if reset else 0))
+
+    def profile(self, enable: bool):
+        check(lib().sab_profile(self._h, 1 if enable else 0, stream_ptr()))
+
+    def profile_report(self) -> dict:
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(lib().sab_profile_report(self._h, buf, len(buf), stream_ptr()))
+        return json.loads(buf.value.decode())
 
     def workspace_bytes(self) -> int:
         return int(lib().sab_workspace_bytes(self._h))

@@ -8,6 +8,7 @@
 #include <functional>
 #include <cmath>
 #include <cstring>
+#include <array>
 
 #include "../../include/samaudio_b200.h"
 #include "host_util.h"
@@ -178,6 +179,7 @@ struct DecBlockW { float* a_up; ConvLayer up; ResUnitW ru[3]; int cin, cout, str
 
 struct DitPlan;
 struct CodecPlan;
+struct ProfRec { const char* tag; double flops; double bytes; };
 
 struct sab_engine {
   sab_config cfg;
@@ -188,6 +190,9 @@ struct sab_engine {
   int64_t staging_elems = 0;
   bool finalized = false;
   int64_t launches = 0;
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_events;
 
   // --- DiT weights ---
   std::vector<LayerW> layers;
@@ -216,7 +221,19 @@ struct sab_engine {
   ~sab_engine();
 };
 
-static inline void count(sab_engine* e, int n = 1) { e->launches += n; }
+// Every kernel launch goes through mark(): it counts the launch and, when profiling is on, drops one event
+// in front of it; the time between consecutive events is attributed to the launch that follows the first.
+static void mark(sab_engine* e, cudaStream_t st, const char* tag, double flops = 0, double bytes = 0) {
+  e->launches++;
+  if (!e->prof) return;
+  if (e->prof_recs.size() >= e->prof_events.size()) {
+    cudaEvent_t ev;
+    SAB_CUDA(cudaEventCreate(&ev));
+    e->prof_events.push_back(ev);
+  }
+  SAB_CUDA(cudaEventRecord(e->prof_events[e->prof_recs.size()], st));
+  e->prof_recs.push_back(ProfRec{tag, flops, bytes});
+}
 
 // =====================================================================================================
 // weight registry
@@ -572,6 +589,7 @@ static void rmsnorm_mod(sab_engine* e, const float* x, const float* w, const flo
                         long long mod_ld, int rows_per_item, bf16* out, int M, cudaStream_t st) {
   const int d = e->cfg.dim;
   const float eps = e->cfg.norm_eps;
+  mark(e, st, "rmsnorm_mod", 0, (double)M * d * 6.0);
   switch (d / 128) {
 #define SAB_RN(v) case v: launch_rmsnorm<v>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps, st); break;
     SAB_RN(2) SAB_RN(4) SAB_RN(8) SAB_RN(12) SAB_RN(16) SAB_RN(20) SAB_RN(22) SAB_RN(24) SAB_RN(32)
@@ -579,7 +597,6 @@ static void rmsnorm_mod(sab_engine* e, const float* x, const float* w, const flo
     default: throw Error(fmt("rmsnorm: unsupported dim %d (add an instantiation)", d));
   }
   SAB_CUDA(cudaGetLastError());
-  count(e);
 }
 
 static void attention(sab_engine* e, const AttnParams& ap, int items, int heads, cudaStream_t st) {
@@ -589,14 +606,14 @@ static void attention(sab_engine* e, const AttnParams& ap, int items, int heads,
     configured = true;
   }
   dim3 grid((ap.Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
+  mark(e, st, ap.k == ap.q ? "sdpa.self" : "sdpa.cross", 4.0 * items * heads * (double)ap.Tq * ap.Tk * 128, 0);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(ap);
   SAB_CUDA(cudaGetLastError());
-  count(e);
 }
 
 static void gemm(sab_engine* e, const GemmOp& op, cudaStream_t st) {
+  mark(e, st, op.tag, op.flops, 0);
   launch_gemm(op, st);
-  count(e);
 }
 
 // final-layer variants: out = base + coef * velocity (ODE axpy fused in the output GEMM's epilogue)
@@ -614,22 +631,26 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
   const int M = (int)p.M;
   const float sl2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
 
-  time_features_kernel<<<256, 256, 0, st>>>(time_dev, Bc, d, L, p.tfreq, p.mem_base, p.mem_in); count(e);
+  mark(e, st, "time_features_kernel");
+  time_features_kernel<<<256, 256, 0, st>>>(time_dev, Bc, d, L, p.tfreq, p.mem_base, p.mem_in);
   gemm(e, p.g_t13, st);
   gemm(e, p.g_t2, st);
-  silu_cast_kernel<<<64, 256, 0, st>>>(p.t, p.t_silu, (long long)Bc * d); count(e);
+  mark(e, st, "silu_cast_kernel");
+  silu_cast_kernel<<<64, 256, 0, st>>>(p.t, p.t_silu, (long long)Bc * d);
   gemm(e, p.g_tb, st);
-  build_mod_kernel<<<512, 256, 0, st>>>(e->tables, p.t0, p.mod, NL, Bc, d, e->final_table, p.t, p.fin); count(e);
+  mark(e, st, "build_mod_kernel");
+  build_mod_kernel<<<512, 256, 0, st>>>(e->tables, p.t0, p.mod, NL, Bc, d, e->final_table, p.t, p.fin);
   gemm(e, p.g_y13, st);
   gemm(e, p.g_y2, st);
   gemm(e, p.g_in, st);
   // x_embedder (patcher.py:138-164): GN(1) -> SiLU -> conv3, twice, + x
   for (int b = 0; b < 2; ++b) {
     const float* src = b == 0 ? p.x0 : p.c1;
-    gn_stats_kernel<<<dim3(GN_CHUNKS, Bc), 256, 0, st>>>(src, (long long)T * d, p.gn_partial); count(e);
+    mark(e, st, "gn_stats_kernel");
+    gn_stats_kernel<<<dim3(GN_CHUNKS, Bc), 256, 0, st>>>(src, (long long)T * d, p.gn_partial);
+    mark(e, st, "gn_silu_kernel");
     gn_silu_kernel<<<dim3(64, Bc), 256, 0, st>>>(src, p.gn_partial, e->xe_gn_w[b], e->xe_gn_b[b], d, (long long)T * d,
                                                1e-5f, p.gn_a);
-    count(e);
     gemm(e, p.g_xe[b], st);
   }
   SAB_CUDA(cudaGetLastError());
@@ -877,6 +898,7 @@ sab_engine::~sab_engine() {
   enc_plans.clear();
   dec_plans.clear();
   if (staging) cudaFree(staging);
+  for (auto ev : prof_events) cudaEventDestroy(ev);
 }
 
 // =====================================================================================================
@@ -1014,21 +1036,24 @@ int sab_prepare(sab_engine* e, int Bc, int T, int L, const float* features, cons
   SAB_CUDA(cudaMemcpyAsync(p.text_mask, text_mask, ML, cudaMemcpyDeviceToDevice, st));
   SAB_CUDA(cudaMemcpyAsync(p.anchor_ids, anchor_ids, (size_t)Bc * n_ids * 8, cudaMemcpyDeviceToDevice, st));
   SAB_CUDA(cudaMemcpyAsync(p.anchor_align, anchor_alignment, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
-  cast_bf16_kernel<<<512, 256, 0, st>>>(features, p.feat_bf, M * 256); count(e);
-  cast_bf16_kernel<<<64, 256, 0, st>>>(text_features, p.text_bf, ML * c.text_dim); count(e);
+  mark(e, st, "cast_bf16_kernel");
+  cast_bf16_kernel<<<512, 256, 0, st>>>(features, p.feat_bf, M * 256);
+  mark(e, st, "cast_bf16_kernel");
+  cast_bf16_kernel<<<64, 256, 0, st>>>(text_features, p.text_bf, ML * c.text_dim);
   gemm(e, p.g_cond, st);
   gemm(e, p.g_mem, st);
   const float* vproj = nullptr;
   if (video_features) {
-    transpose_cast_kernel<<<1024, 256, 0, st>>>(video_features, c.vision_dim, T, M * c.vision_dim, p.vid_bf); count(e);
+    mark(e, st, "transpose_cast_kernel");
+    transpose_cast_kernel<<<1024, 256, 0, st>>>(video_features, c.vision_dim, T, M * c.vision_dim, p.vid_bf);
     gemm(e, p.g_vid, st);
     vproj = p.vproj;
   }
+  mark(e, st, "cond_finish_kernel");
   cond_finish_kernel<<<(int)((M + 7) / 8), 256, 0, st>>>(p.cond, (int)M, d, T, vproj, e->vid_ln_w, e->vid_ln_b, e->vid_const,
                                                         e->vid_gate, e->anchor_table,
                                                         reinterpret_cast<const long long*>(p.anchor_ids), n_ids,
                                                         reinterpret_cast<const long long*>(p.anchor_align), e->anchor_gate);
-  count(e);
   SAB_CUDA(cudaGetLastError());
   SAB_API_END
 }
@@ -1038,7 +1063,8 @@ int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float*
   SAB_CHECK(e && e->dit, "sab_prepare must be called first");
   cudaStream_t st = (cudaStream_t)stream;
   DitPlan& p = *e->dit;
-  cast_bf16_kernel<<<512, 256, 0, st>>>(noisy, p.y_bf, p.M * 256); count(e);
+  mark(e, st, "cast_bf16_kernel");
+  cast_bf16_kernel<<<512, 256, 0, st>>>(noisy, p.y_bf, p.M * 256);
   FinalSpec fs{nullptr, 1.f, velocity, nullptr};
   dit_eval(e, time, fs, st);
   SAB_API_END
@@ -1061,7 +1087,8 @@ int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, voi
   SAB_CUDA(cudaMemcpyAsync(p.time_dev, times.data(), times.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   SAB_CUDA(cudaStreamSynchronize(st));  // `times` is a stack-owned host buffer
   SAB_CUDA(cudaMemcpyAsync(p.y, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  cast_bf16_kernel<<<512, 256, 0, st>>>(p.y, p.y_bf, n); count(e);
+  mark(e, st, "cast_bf16_kernel");
+  cast_bf16_kernel<<<512, 256, 0, st>>>(p.y, p.y_bf, n);
   const float dt = 1.0f / (float)n_steps;
   for (int k = 0; k < n_steps; ++k) {
     // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)
@@ -1082,23 +1109,23 @@ static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_
       case CodecStep::ENC0: {
         const int C0 = c.codec_encoder_dim;
         const long long n = cp.S * (C0 / 4);
+        mark(e, st, "codec.enc.conv0", 2.0 * items * (double)cp.S * C0 * 7, (double)items * cp.S * (4.0 + C0 * 6.0));
         enc_conv0_kernel<<<dim3((unsigned)((n + 255) / 256), items), 256, 0, st>>>(
             wav_in, cp.S, C0, e->enc0_w, e->enc0_b, e->enc_blocks[0].ru[0].a0, cp.x_first, cp.a_first);
-        count(e);
         break;
       }
       case CodecStep::LATENT_SPLIT: {
         const int cz = c.codec_codebook_dim;
+        mark(e, st, "latent_split_kernel");
         latent_split_kernel<<<512, 256, 0, st>>>(latent_in, T, cz, (long long)items * T * cz, cp.z_in);
-        count(e);
         break;
       }
       case CodecStep::DEC_LAST: {
         const int C = c.codec_decoder_dim >> c.codec_n_rates;
         const int smem = ((DEC_LAST_TB + 6) * (C + 2) + 2) * 2 + 7 * C * 4;
+        mark(e, st, "codec.dec.last", 2.0 * items * (double)cp.S * C * 7, (double)items * cp.S * (4.0 + C * 2.0));
         dec_last_kernel<<<dim3((unsigned)((cp.S + DEC_LAST_TB - 1) / DEC_LAST_TB), items), DEC_LAST_TB, smem, st>>>(
             cp.a_last, cp.S, C, e->dec_last_w, e->dec_last_b, out);
-        count(e);
         break;
       }
       default: {
@@ -1107,6 +1134,7 @@ static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_
         if (&s.op == cp.enc_out) op.P.out_f32 = out;
         const long long tiles = (long long)items * op.P.tiles_per_item * op.P.n_tiles_n;
         op.grid = (int)std::min<long long>(tiles, g_sm_count);
+        op.flops = s.op.flops * (double)items / (double)cp.items;
         gemm(e, op, st);
       }
     }
@@ -1175,6 +1203,51 @@ int64_t sab_workspace_bytes(sab_engine* e) {
   for (auto& kv : e->enc_plans) b += kv.second->pool.bytes;
   for (auto& kv : e->dec_plans) b += kv.second->pool.bytes;
   return b;
+}
+
+int sab_profile(sab_engine* e, int enable, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e, "null engine");
+  SAB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->prof = enable != 0;
+  e->prof_recs.clear();
+  SAB_API_END
+}
+
+// JSON: {"tag": {"launches": n, "ms": t, "flops": f, "bytes": b}, ...} aggregated since sab_profile(e, 1).
+int sab_profile_report(sab_engine* e, char* buf, int64_t cap, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(e && buf && cap > 2, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = e->prof_recs.size();
+  std::map<std::string, std::array<double, 4>> agg;
+  if (n > 0) {
+    if (e->prof_events.size() <= n) {
+      cudaEvent_t ev;
+      SAB_CUDA(cudaEventCreate(&ev));
+      e->prof_events.push_back(ev);
+    }
+    SAB_CUDA(cudaEventRecord(e->prof_events[n], st));
+    SAB_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      SAB_CUDA(cudaEventElapsedTime(&ms, e->prof_events[i], e->prof_events[i + 1]));
+      auto& a = agg[e->prof_recs[i].tag];
+      a[0] += 1; a[1] += ms; a[2] += e->prof_recs[i].flops; a[3] += e->prof_recs[i].bytes;
+    }
+  }
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    js += fmt("%s\"%s\": {\"launches\": %.0f, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+              kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2], kv.second[3]);
+    first = false;
+  }
+  js += "}";
+  SAB_CHECK((int64_t)js.size() + 1 <= cap, "profile buffer too small (%zu needed)", js.size() + 1);
+  memcpy(buf, js.c_str(), js.size() + 1);
+  e->prof_recs.clear();
+  SAB_API_END
 }
 
 // ---- test seams ----

@@ -43,16 +43,16 @@ def fold_weight_norm(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Ten
     out: Dict[str, torch.Tensor] = {}
     pending: Dict[str, Dict[str, torch.Tensor]] = {}
     for k, v in state_dict.items():
-        m = re.match(r"^(.*)\.(weight_g|weight_v|parametrizations\.weight\.original[01])$", k)
+        m = re.match(r"^(?:(.*)\.)?(weight_g|weight_v|parametrizations\.weight\.original[01])$", k)
         if not m:
             out[k] = v
             continue
         kind = "g" if m.group(2) in ("weight_g", "parametrizations.weight.original0") else "v"
-        pending.setdefault(m.group(1), {})[kind] = v
+        pending.setdefault(m.group(1) or "", {})[kind] = v
     for base, gv in pending.items():
         g, v = gv["g"].float(), gv["v"].float()
         norm = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
-        out[f"{base}.weight"] = g * v / norm
+        out[f"{base}.weight" if base else "weight"] = g * v / norm
     return out
 
 

@@ -1,0 +1,104 @@
+"""Data-parallel sharding of separate() over the GPUs of one box.
+
+The path is embarrassingly parallel over clips (the reference's only
+parallelism is a DistributedSampler over clips with a full model replica per rank,
+eval/main.py:53-76).  One process per GPU over ``torch.distributed``:
+
+* ``broadcast_state_dict`` — one broadcast of the (flattened) weights from rank 0
+  (NCCL over NVLink on GPUs, gloo in the CPU tests);
+* ``shard_range`` — contiguous split of the clips; a clip's candidates stay on one rank;
+* ``all_gather_waveforms`` — one all-gather of the separated waveforms.
+
+No collective sits inside the model: the ODE loop never communicates.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of rank's items; the first (n % world) ranks take one extra."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def broadcast_state_dict(sd: Dict[str, torch.Tensor] | None, src: int = 0, device="cpu",
+                         group=None) -> Dict[str, torch.Tensor]:
+    """Rank ``src`` holds ``sd``; every rank returns an identical fp32 copy on ``device``.
+    Metadata travels as one object broadcast, the payload as ONE flat tensor broadcast."""
+    rank = dist.get_rank(group)
+    meta = [None]
+    if rank == src:
+        assert sd is not None
+        meta[0] = [(k, tuple(v.shape)) for k, v in sd.items()]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    total = sum(int(torch.Size(s).numel()) for _, s in meta[0])
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    if rank == src:
+        off = 0
+        for k, s in meta[0]:
+            n = int(torch.Size(s).numel())
+            flat[off:off + n] = sd[k].reshape(-1).to(device=device, dtype=torch.float32)
+            off += n
+    dist.broadcast(flat, src=src, group=group)
+    out, off = {}, 0
+    for k, s in meta[0]:
+        n = int(torch.Size(s).numel())
+        out[k] = flat[off:off + n].view(s)
+        off += n
+    return out
+
+
+def all_gather_waveforms(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """local [n_local, 2, S] -> [sum(counts), 2, S] on every rank (one all-gather; ragged shards are
+    padded to the largest and trimmed)."""
+    world = dist.get_world_size(group)
+    n_max = max(counts)
+    if local.shape[0] < n_max:
+        pad = local.new_zeros(n_max - local.shape[0], *local.shape[1:])
+        local = torch.cat([local, pad], 0)
+    buf = local.new_empty(world * n_max, *local.shape[1:])
+    dist.all_gather_into_tensor(buf, local.contiguous(), group=group)
+    if all(c == n_max for c in counts):
+        return buf
+    parts = [buf[r * n_max: r * n_max + counts[r]] for r in range(world)]
+    return torch.cat(parts, 0)
+
+
+def separate_sharded(model, processor, descriptions: List[str], audios: List[torch.Tensor], noise=None,
+                     reranking_candidates: int = 1, group=None):
+    """Every rank passes the same full clip list; each separates its contiguous shard and all ranks
+    return the full, ordered (target, residual) lists.  Clips are equal-length-padded per shard exactly as
+    the single-process call would pad them, so results match a single-GPU run clip for clip."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = len(audios)
+    lo, hi = shard_range(n, rank, world)
+    counts = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+    dev = model.device()
+    hop = processor.audio_hop_length
+    longest = max(a.shape[-1] for a in audios)
+    S = ((longest + hop - 1) // hop) * hop
+    local = torch.zeros(max(hi - lo, 0), 2, S, device=dev)
+    if hi > lo:
+        # pad the shard to the global longest clip so that every rank's T matches the 1-GPU batch
+        batch = processor(descriptions=descriptions[lo:hi], audios=audios[lo:hi])
+        if batch.audios.shape[-1] < longest:
+            batch.audios = torch.nn.functional.pad(batch.audios, (0, longest - batch.audios.shape[-1]))
+            full = torch.zeros(hi - lo, (longest + hop - 1) // hop, dtype=torch.bool)
+            full[:, : batch.audio_pad_mask.shape[1]] = batch.audio_pad_mask
+            batch.audio_pad_mask = full
+            batch.process_anchors(batch.anchors)
+        batch = batch.to(dev)
+        c = reranking_candidates
+        nz = None if noise is None else noise[lo * c: hi * c].to(dev)
+        out = model.separate(batch, noise=nz, reranking_candidates=c)
+        for i, (t, r) in enumerate(zip(out.target, out.residual)):
+            local[i, 0, : t.numel()] = t
+            local[i, 1, : r.numel()] = r
+    full = all_gather_waveforms(local, counts, group=group)
+    sizes = [((a.shape[-1] + hop - 1) // hop) * hop for a in audios]
+    return [full[i, 0, : sizes[i]] for i in range(n)], [full[i, 1, : sizes[i]] for i in range(n)]

@@ -1,0 +1,194 @@
+"""GPU (B200) parity tests — the CUDA path, called through the C ABI (ctypes) and the public Python
+mirror, against (a) golden vectors produced by the reference's own code, (b) the CPU oracle on the same
+seeded inputs, and (c) size-independent properties at the full 10 s / 48 kHz clip size.
+
+Tolerances (bf16 tensor-core operands, fp32 accumulation and fp32 residual streams; the reference is fp32):
+  * single GEMM vs fp32 matmul of the same bf16-rounded operands ............ rel-L2 <= 1e-3
+  * attention (bf16 P, bf16 output) ........................................ rel-L2 <= 1e-2
+  * one DiT evaluation vs reference ........................................ rel-L2 <= 2e-2
+  * codec encode / decode vs oracle ........................................ rel-L2 <= 2e-2 / 3e-2
+  * separate() waveforms vs reference (32 evaluations compound) ............ SNR >= 30 dB
+  * integer outputs (sizes, lengths, masks, anchors) ....................... bit-exact
+"""
+import os
+
+import pytest
+import torch
+
+from _util import rel_l2, snr_db
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import __graft_entry__ as g
+    g.build()
+    from sam_audio_b200 import _capi
+    assert torch.cuda.is_available()
+    return _capi
+
+
+@pytest.mark.parametrize("M,N,K,bn,bk", [
+    (128, 256, 64, 256, 64), (300, 256, 256, 256, 64), (1000, 512, 2048, 128, 64), (2500, 2048, 2048, 256, 64),
+    (300, 96, 96, 96, 32), (777, 128, 160, 128, 32), (500, 192, 192, 192, 64), (333, 96, 192, 96, 64),
+    (129, 64, 128, 64, 64), (1, 256, 64, 256, 64)])
+def test_tcgen05_gemm(capi, M, N, K, bn, bk):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    c = torch.full((M, N), float("nan"), device="cuda")
+    capi.check(capi.lib().sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), bn, bk, capi.stream_ptr()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(c).any()
+    assert rel_l2(c, a.float() @ b.float().t()) < 1e-3
+
+
+@pytest.mark.parametrize("items,heads,Tq,Tk", [(2, 2, 64, 64), (2, 3, 250, 250), (3, 2, 37, 5), (1, 2, 300, 130),
+                                               (1, 1, 1, 1), (2, 2, 250, 512)])
+def test_attention(capi, items, heads, Tq, Tk):
+    g = torch.Generator(device="cuda").manual_seed(Tq + Tk)
+    q, k, v = (torch.randn(items * t, heads * 128, device="cuda", generator=g).bfloat16() for t in (Tq, Tk, Tk))
+    mask = torch.ones(items, Tk, dtype=torch.uint8, device="cuda")
+    for i in range(items):
+        mask[i, max(1, Tk - 3 * (i + 1)):] = 0
+    o = torch.zeros(items * Tq, heads * 128, device="cuda", dtype=torch.bfloat16)
+    capi.check(capi.lib().sab_test_attention(items, heads, Tq, Tk, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                             mask.data_ptr(), o.data_ptr(), capi.stream_ptr()))
+    torch.cuda.synchronize()
+    qf, kf, vf = (x.float().view(items, -1, heads, 128).permute(0, 2, 1, 3) for x in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2) / 128 ** 0.5).masked_fill(~mask.bool()[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(items * Tq, heads * 128)
+    assert rel_l2(o.float(), ref) < 1e-2
+
+
+def test_dit_evaluation_vs_reference_golden(tiny_model, golden_dir):
+    """SAMAudio.forward (ragged pad mask, text mask, anchors, with and without video) vs the reference's
+    own SAMAudio.forward output (tests/golden/samaudio_forward_tiny.pt)."""
+    g = torch.load(os.path.join(golden_dir, "samaudio_forward_tiny.pt"))
+    for tag, vid in (("video", g["video"]), ("novideo", None)):
+        out = tiny_model.forward(g["noisy"].cuda(), g["feats"].cuda(), g["text"].cuda(), g["time"].cuda(),
+                                 masked_video_features=None if vid is None else vid.cuda(),
+                                 text_mask=g["text_mask"].cuda(), anchor_ids=g["anchor_ids"].cuda(),
+                                 anchor_alignment=g["anchor_alignment"].cuda(), audio_pad_mask=g["pad_mask"].cuda())
+        assert rel_l2(out.cpu(), g["out"][tag]) < 2e-2, tag
+
+
+def test_codec_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
+    from oracle import restate
+    from sam_audio_b200.synthetic import synthetic_clip
+    wav = torch.stack([synthetic_clip(i, 1920 * 11 + 300) for i in range(3)])      # not a hop multiple -> reflect pad
+    ref = restate.codec_encode(tiny_sd, tiny_cfg.audio_codec, wav).transpose(1, 2)
+    feats = tiny_model._get_audio_features(wav.cuda())
+    assert feats.shape == (3, 12, 256)
+    assert torch.equal(feats[:, :, :128], feats[:, :, 128:])                       # model.py:183-184 duplication
+    assert rel_l2(feats[:, :, :128].cpu(), ref) < 2e-2
+    lat = torch.randn(3, 12, 256, generator=torch.Generator().manual_seed(3))
+    ref_w = restate.codec_decode(tiny_sd, tiny_cfg.audio_codec, lat.transpose(1, 2).reshape(6, 128, 12)).view(3, 2, -1)
+    out = torch.empty(3, 2, 12 * 1920, device="cuda")
+    tiny_model._ensure_engine().decode(lat.cuda(), 3, 12, out)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref_w) < 3e-2 and float(out.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("cand", [1, 2])
+def test_separate_vs_reference_golden(tiny_model, golden_dir, cand):
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_descriptions
+    g = torch.load(os.path.join(golden_dir, "separate_tiny.pt"))
+    proc = SAMAudioProcessor(1920, 48000)
+    auds = [synthetic_clip(i, n) for i, n in enumerate(g["lens"])]
+    batch = proc(descriptions=synthetic_descriptions(2), audios=auds).to("cuda")
+    r = g["results"][cand]
+    out = tiny_model.separate(batch, noise=r["noise"].cuda(), reranking_candidates=cand)
+    assert torch.equal(out.noise.cpu(), r["noise"])
+    for ours, ref in zip(list(out.target) + list(out.residual), list(r["target"]) + list(r["residual"])):
+        assert ours.shape == ref.shape                      # lengths = sizes*1920, bit-exact
+        assert snr_db(ours.cpu(), ref) > 30.0
+
+
+def test_separate_with_anchors_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
+    from oracle import restate
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.synthetic import (synthetic_clip, synthetic_descriptions, synthetic_noise,
+                                          synthetic_text_features)
+    proc = SAMAudioProcessor(1920, 48000)
+    lens = [7000, 9600, 1921]
+    auds = [synthetic_clip(10 + i, n) for i, n in enumerate(lens)]
+    anchors = [[["+", 0.02, 0.1]], [["-", 0.0, 0.05], ["+", 0.04, 0.2]], []]
+    desc = synthetic_descriptions(3)
+    host = proc(descriptions=desc, audios=auds, anchors=anchors)
+    noise = synthetic_noise(3, int(host.sizes.max()))
+    out = tiny_model.separate(proc(descriptions=desc, audios=auds, anchors=anchors).to("cuda"), noise=noise.cuda())
+    tf, tm = synthetic_text_features(desc)
+    tgt, res = restate.separate(tiny_sd, tiny_cfg, host.audios, host.audio_pad_mask, host.sizes, tf, tm,
+                                host.anchor_ids, host.anchor_alignment, noise)
+    for ours, ref in zip(list(out.target) + list(out.residual), tgt + res):
+        assert ours.shape == ref.shape and snr_db(ours.cpu(), ref) > 30.0
+
+
+def test_solver_composition_and_determinism(tiny_model):
+    """sab_solve(n_steps=1) == the midpoint formula composed from two sab_dit_forward calls; repeated
+    solves are bit-identical (no atomics / nondeterministic reductions on the path)."""
+    g = torch.Generator().manual_seed(11)
+    B, T, L = 2, 20, 4
+    feats = torch.randn(B, T, 128, generator=g)
+    feats = torch.cat([feats, feats], 2).cuda()
+    text = torch.randn(B, L, 768, generator=g).cuda()
+    ids = torch.tensor([[0, 3]] * B).cuda()
+    al = torch.zeros(B, T, dtype=torch.long).cuda()
+    y0 = torch.randn(B, T, 256, generator=g).cuda()
+    eng = tiny_model._ensure_engine()
+    tiny_model._install_conditioning(feats, text, None, None, ids, al, None)
+    a = torch.empty_like(y0)
+    eng.solve(y0, 1, a)
+    b = torch.empty_like(y0)
+    eng.solve(y0, 1, b)
+    assert torch.equal(a, b)
+    f0 = torch.empty_like(y0)
+    eng.dit_forward(y0, torch.zeros(B, device="cuda"), f0)
+    f1 = torch.empty_like(y0)
+    eng.dit_forward(y0 + 0.5 * f0, torch.full((B,), 0.5, device="cuda"), f1)
+    assert rel_l2(a, y0 + f1) < 5e-3
+
+
+def test_missing_or_unknown_weights_fail_loudly(tiny_cfg, tiny_sd):
+    from sam_audio_b200.model import SAMAudio
+    from sam_audio_b200.text_encoder import SyntheticTextEncoder
+    m = SAMAudio(tiny_cfg, text_encoder=SyntheticTextEncoder()).cuda()
+    sd = dict(tiny_sd)
+    sd.pop("transformer.layers.1.feed_forward.w2.weight")
+    m.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="Missing keys"):
+        m._ensure_engine()
+    m2 = SAMAudio(tiny_cfg, text_encoder=SyntheticTextEncoder()).cuda()
+    sd2 = dict(tiny_sd)
+    sd2["transformer.bogus.weight"] = torch.zeros(3)
+    m2.load_state_dict(sd2)
+    with pytest.raises(RuntimeError, match="unexpected weight"):
+        m2._ensure_engine()
+    m3 = SAMAudio(tiny_cfg, text_encoder=SyntheticTextEncoder())
+    m3.load_state_dict(tiny_sd)
+    with pytest.raises(RuntimeError, match="B200 only"):
+        m3._ensure_engine()                                  # still on CPU: no fallback
+
+
+def test_full_size_properties_10s_clips(tiny_model):
+    """BASELINE clip size (10 s @ 48 kHz, T = 250): properties that do not need the (slow) CPU oracle.
+      * batch invariance: a clip separated alone == the same clip inside a batch (every op is per-sequence);
+      * candidates: duplicated noise rows give identical candidates;
+      * outputs are finite, bounded by tanh, and of length sizes*1920 exactly."""
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_descriptions, synthetic_noise
+    proc = SAMAudioProcessor(1920, 48000)
+    auds = [synthetic_clip(i) for i in range(3)]
+    desc = synthetic_descriptions(3)
+    noise = synthetic_noise(3, 250).cuda()
+    full = tiny_model.separate(proc(descriptions=desc, audios=auds).to("cuda"), noise=noise)
+    one = tiny_model.separate(proc(descriptions=desc[1:2], audios=auds[1:2]).to("cuda"), noise=noise[1:2])
+    assert full.target[1].shape == (480000,) and torch.isfinite(full.target[1]).all()
+    assert float(full.target[1].abs().max()) <= 1.0
+    assert torch.equal(full.target[1], one.target[0]) and torch.equal(full.residual[1], one.residual[0])
+    n2 = noise[:1].repeat_interleave(2, 0)
+    c2 = tiny_model.separate(proc(descriptions=desc[:1], audios=auds[:1]).to("cuda"), noise=n2, reranking_candidates=2)
+    assert torch.equal(c2.target[0], full.target[0])

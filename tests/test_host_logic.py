@@ -1,0 +1,75 @@
+"""CPU: host-side logic of the drop-in mirror (config, weight-norm folding, synthetic shapes, sharding)."""
+import math
+
+import pytest
+import torch
+
+from sam_audio_b200.config import SAMAudioConfig, TransformerConfig, stand_in_config
+from sam_audio_b200.model import DFLT_ODE_OPT, fold_weight_norm
+from sam_audio_b200.parallel import shard_range
+from sam_audio_b200.synthetic import codec_param_shapes, make_state_dict
+
+
+def test_reference_defaults():
+    c = SAMAudioConfig()
+    t = c.transformer
+    assert (t.dim, t.n_heads, t.n_layers, t.head_dim) == (2048, 16, 16, 128)
+    assert t.ffn_hidden == 5504 and t.rope_theta == 20000.0        # transformer.py:179-185, :405-406
+    assert c.audio_codec.hop_length == 1920 and c.in_channels == 768
+    assert DFLT_ODE_OPT == {"method": "midpoint", "options": {"step_size": 2 / 32}}
+    assert stand_in_config("sam-audio-large").transformer.ffn_hidden == 7552
+
+
+def test_config_roundtrip_uses_reference_json_keys():
+    c = SAMAudioConfig(transformer={"dim": 1536, "n_heads": 12, "n_layers": 12, "context_dim": 1536})
+    d = c.to_dict()
+    assert set(d) == {"in_channels", "audio_codec", "text_encoder", "vision_encoder", "transformer", "num_anchors",
+                      "anchor_embedding_dim", "visual_ranker", "text_ranker", "span_predictor"}
+    c2 = SAMAudioConfig(**d)
+    assert c2.transformer.dim == 1536 and c2.audio_codec.encoder_rates == [2, 8, 10, 12]
+
+
+def test_unsupported_variants_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        TransformerConfig(dim=1024, n_heads=16).check_supported()        # head_dim 64
+    with pytest.raises(NotImplementedError):
+        TransformerConfig(non_linearity="gelu").check_supported()
+    TransformerConfig().check_supported()
+
+
+def test_fold_weight_norm_both_spellings():
+    g, v = torch.rand(4, 1, 1) + 0.5, torch.randn(4, 3, 7)
+    w = g * v / v.flatten(1).norm(dim=1).view(4, 1, 1)
+    a = fold_weight_norm({"x.weight_g": g, "x.weight_v": v, "x.bias": torch.zeros(4)})
+    b = fold_weight_norm({"x.parametrizations.weight.original0": g, "x.parametrizations.weight.original1": v})
+    assert torch.allclose(a["x.weight"], w) and torch.allclose(b["x.weight"], w) and "x.bias" in a
+    ref = torch.nn.utils.parametrizations.weight_norm(torch.nn.Conv1d(3, 4, 7))
+    sd = ref.state_dict()
+    assert torch.allclose(fold_weight_norm(sd)["weight"], ref.weight, atol=1e-6)
+
+
+def test_synthetic_state_dict_names_and_shapes():
+    cfg = stand_in_config("sam-audio-tiny")
+    sd = make_state_dict(cfg, seed=0)
+    d, hid = 256, cfg.transformer.ffn_hidden
+    assert sd["transformer.layers.1.feed_forward.w1.weight"].shape == (hid, d)
+    assert sd["transformer.x_embedder.block.block2.project.weight"].shape == (d, d, 3)
+    assert sd["transformer.t_block.weight"].shape == (6 * d, d)
+    assert sd["proj.weight"].shape == (d, 768)
+    assert sd["audio_codec.decoder.model.1.block.1.weight"].shape == (1536, 768, 24)
+    assert sd["audio_codec.encoder.block.4.block.4.weight"].shape == (1024, 512, 24)
+    assert sd["audio_codec.quantizer.in_proj.weight"].shape == (256, 1024, 1)
+    n_codec = sum(math.prod(s) for _, s, _ in codec_param_shapes(cfg.audio_codec))
+    assert 60e6 < n_codec < 120e6
+    sd2 = make_state_dict(cfg, seed=0)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)               # deterministic across calls
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 7, 8, 256):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
