@@ -108,8 +108,9 @@ int sab_profile(sab_engine* e, int enable, void* stream);
 int sab_profile_report(sab_engine* e, char* json_out, int64_t capacity, void* stream);
 
 /* ---- unit-test seams (used by tests/ only; stable but not part of the drop-in surface) ---- */
-/* C[M,N] (fp32) = A[M,K] (bf16) * B[N,K]^T (bf16) through the tcgen05 GEMM (BN = 128 or 256, BK = 64 or 32). */
-int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk,
+/* C[M,N] (fp32) = A[M,K] (bf16) * B[N,K]^T (bf16) through the tcgen05 GEMM (tile BN x BK; cg = 1: one CTA per
+ * 128-row tile, cg = 2: cta_group::2 pairs on 256-row tiles, cg = 0: the engine's default choice). */
+int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk, int cg,
                   void* stream);
 /* O = softmax(Q K^T / sqrt(128) + mask) V through the attention kernel; all [items*T, heads*128] bf16. */
 int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, const void* k, const void* v,

@@ -67,7 +67,7 @@ def lib() -> ctypes.CDLL:
         L.sab_workspace_bytes.restype = i64
         L.sab_profile.argtypes = [vp, i32, vp]
         L.sab_profile_report.argtypes = [vp, ctypes.c_char_p, i64, vp]
-        L.sab_test_gemm.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, vp]
+        L.sab_test_gemm.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
         L.sab_test_attention.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib

@@ -8,6 +8,7 @@
 #include <functional>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <array>
 
 #include "../../include/samaudio_b200.h"
@@ -25,33 +26,53 @@ static int g_sm_count = 0;
 // =====================================================================================================
 // GEMM dispatch
 // =====================================================================================================
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, int CG>
 static void launch_gemm_inst(const GemmOp& op, cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, BK, MODE>;
+  auto kern = gemm_tc_kernel<BN, BK, MODE, CG>;
+  constexpr int smem = GemmSmem<BN, BK, CG>::kTotal;
   if (!configured) {
-    SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BK>::kTotal));
+    SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<op.grid, GEMM_THREADS, GemmSmem<BN, BK>::kTotal, st>>>(op.tmA, op.tmB, op.P);
+  if (CG == 1) {
+    kern<<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, op.P);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(op.grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SAB_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.P));
+  }
   SAB_CUDA(cudaGetLastError());
 }
 
 static void launch_gemm(const GemmOp& op, cudaStream_t st) {
-#define SAB_CASE(bn, bk, md) \
-  if (op.BN == bn && op.BK == bk && op.mode == md) return launch_gemm_inst<bn, bk, md>(op, st);
-  SAB_CASE(256, 64, EPI_AFFINE)
-  SAB_CASE(192, 64, EPI_AFFINE)
-  SAB_CASE(128, 64, EPI_AFFINE)
-  SAB_CASE(96, 64, EPI_AFFINE)
-  SAB_CASE(64, 64, EPI_AFFINE)
-  SAB_CASE(96, 32, EPI_AFFINE)
-  SAB_CASE(128, 32, EPI_AFFINE)
-  SAB_CASE(256, 64, EPI_SWIGLU)
-  SAB_CASE(256, 64, EPI_QKV)
-  SAB_CASE(128, 64, EPI_QKV)
+#define SAB_CASE(bn_, bk_, md_, cg_) \
+  if (op.BN == bn_ && op.BK == bk_ && op.mode == md_ && op.cg == cg_) return launch_gemm_inst<bn_, bk_, md_, cg_>(op, st);
+  SAB_CASE(256, 64, EPI_AFFINE, 2)
+  SAB_CASE(256, 64, EPI_SWIGLU, 2)
+  SAB_CASE(256, 64, EPI_QKV, 2)
+  SAB_CASE(256, 64, EPI_AFFINE, 1)
+  SAB_CASE(192, 64, EPI_AFFINE, 1)
+  SAB_CASE(128, 64, EPI_AFFINE, 1)
+  SAB_CASE(96, 64, EPI_AFFINE, 1)
+  SAB_CASE(64, 64, EPI_AFFINE, 1)
+  SAB_CASE(96, 32, EPI_AFFINE, 1)
+  SAB_CASE(128, 32, EPI_AFFINE, 1)
+  SAB_CASE(256, 64, EPI_SWIGLU, 1)
+  SAB_CASE(256, 64, EPI_QKV, 1)
+  SAB_CASE(128, 64, EPI_QKV, 1)
 #undef SAB_CASE
-  throw Error(fmt("no GEMM instantiation for BN=%d BK=%d mode=%d (%s)", op.BN, op.BK, op.mode, op.tag));
+  throw Error(fmt("no GEMM instantiation for BN=%d BK=%d mode=%d cg=%d (%s)", op.BN, op.BK, op.mode, op.cg, op.tag));
 }
 
 // A operand view
@@ -83,23 +104,36 @@ struct RunList {
   }
 };
 
+static int g_force_cg = 0;   // SAB_FORCE_CG=1|2 overrides the CTA-group choice (A/B measurements)
+
 static GemmOp make_gemm(const char* tag, const AView& A, const bf16* B, int N, int BN, int BK, int mode,
-                        const RunList& runs) {
+                        const RunList& runs, int cg = 0) {
   GemmOp op;
   memset(&op.P, 0, sizeof(op.P));
   op.tag = tag;
   op.BN = BN; op.BK = BK; op.mode = mode;
+  // 2-CTA pairs (cta_group::2, 256 x BN tiles) for the big tensor-bound GEMMs
+  if (cg == 0) cg = (BN == 256 && BK == 64 && A.rows * A.items >= 1024 && A.rows >= 200) ? 2 : 1;
+  if (g_force_cg && BN == 256 && BK == 64) cg = g_force_cg;
+  op.cg = cg;
   const int ktot = runs.total_kb(0) * BK;
   if (runs.period > 0) SAB_CHECK(runs.total_kb(1) * BK == ktot, "%s: run lists differ in K", tag);
   op.tmA = make_tmap_3d(A.ptr, A.cols, A.rows, A.items, A.row_pitch, A.item_pitch == 0 ? A.rows * A.row_pitch : A.item_pitch,
                         BK, GEMM_BM);
-  op.tmB = make_tmap_2d(B, ktot, N, ktot, BK, BN);
+  op.tmB = make_tmap_2d(B, ktot, N, ktot, BK, BN / cg);
   GemmParams& P = op.P;
   P.rows_per_item = (int)A.rows;
   P.n_items = (int)A.items;
-  P.tiles_per_item = (int)((A.rows + GEMM_BM - 1) / GEMM_BM);
+  P.tiles_per_item = (int)((A.rows + GEMM_BM * cg - 1) / (GEMM_BM * cg));
   P.N = N;
   P.n_tiles_n = (N + BN - 1) / BN;
+  // rasterisation: keep one group's A panel (group_m x 128*cg x K bf16) around 24 MB so it stays L2-resident
+  {
+    const double panel_bytes = (double)GEMM_BM * cg * ktot * 2.0;
+    int gm = (int)(24.0e6 / panel_bytes);
+    gm = gm < 4 ? 4 : (gm > 32 ? 32 : gm);
+    P.group_m = gm;
+  }
   for (int l = 0; l < 2; ++l) {
     P.n_runs[l] = runs.n[l];
     for (int i = 0; i < runs.n[l]; ++i) P.runs[l][i] = runs.r[l][i];
@@ -111,7 +145,7 @@ static GemmOp make_gemm(const char* tag, const AView& A, const bf16* B, int N, i
   P.gate_div = 1;
   P.eps = 1e-5f;
   const long long tiles = (long long)P.n_items * P.tiles_per_item * P.n_tiles_n;
-  op.grid = (int)std::min<long long>(tiles, g_sm_count);
+  op.grid = (int)std::min<long long>(tiles, g_sm_count / cg) * cg;
   op.flops = 2.0 * (double)A.rows * (double)A.items * (double)N * (double)ktot;
   SAB_CHECK(N % 32 == 0, "%s: N=%d must be a multiple of 32", tag, N);
   return op;
@@ -930,6 +964,7 @@ int sab_create(const sab_config* cfg, int device, sab_engine** out) {
   SAB_CUDA(cudaGetDeviceProperties(&prop, device));
   SAB_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
+  if (const char* f = getenv("SAB_FORCE_CG")) g_force_cg = atoi(f);
   SAB_CHECK(cfg->dim % 128 == 0 && cfg->dim / cfg->n_heads == 128, "dim must be n_heads*128");
   SAB_CHECK(cfg->ffn_hidden % 64 == 0, "ffn_hidden must be a multiple of 64");
   SAB_CHECK(cfg->codec_n_rates >= 1 && cfg->codec_n_rates <= 8, "bad codec_n_rates");
@@ -1133,7 +1168,7 @@ static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_
         op.P.n_items = items;
         if (&s.op == cp.enc_out) op.P.out_f32 = out;
         const long long tiles = (long long)items * op.P.tiles_per_item * op.P.n_tiles_n;
-        op.grid = (int)std::min<long long>(tiles, g_sm_count);
+        op.grid = (int)std::min<long long>(tiles, g_sm_count / op.cg) * op.cg;
         op.flops = s.op.flops * (double)items / (double)cp.items;
         gemm(e, op, st);
       }
@@ -1251,7 +1286,8 @@ int sab_profile_report(sab_engine* e, char* buf, int64_t cap, void* stream) {
 }
 
 // ---- test seams ----
-int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk, void* stream) {
+int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk, int cg,
+                  void* stream) {
   SAB_API_BEGIN
   if (!g_sm_count) {
     cudaDeviceProp prop;
@@ -1261,7 +1297,7 @@ int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, f
   RunList rl;
   SAB_CHECK(K % bk == 0, "K must be a multiple of bk");
   rl.add(0, 0, 0, K / bk);
-  GemmOp op = make_gemm("test", flat_view((const bf16*)a_bf16, M, K), (const bf16*)b_bf16, N, bn, bk, EPI_AFFINE, rl);
+  GemmOp op = make_gemm("test", flat_view((const bf16*)a_bf16, M, K), (const bf16*)b_bf16, N, bn, bk, EPI_AFFINE, rl, cg);
   op.P.out_f32 = c; op.P.out_f32_ld = N;
   launch_gemm(op, (cudaStream_t)stream);
   SAB_API_END

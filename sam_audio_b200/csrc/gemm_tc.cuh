@@ -6,9 +6,18 @@
 //    (one run per tap; TMA zero-fills rows that fall off either end of an item = the conv's padding).
 //  * B (weights, bf16, [N, Ktot] K-major, packed at load time) arrives through a 2-D TMA map.
 //  * Accumulators live in TMEM (2 x BN fp32 columns, double buffered): the epilogue of tile i
-//    overlaps the MMAs of tile i+1.  One elected thread issues tcgen05.mma (M=128, N=BN, K=16).
+//    overlaps the MMAs of tile i+1.  One elected thread issues tcgen05.mma (K=16 per instruction).
+//  * CG = 1: one CTA per 128 x BN tile (M=128 UMMA).
+//    CG = 2: a 2-CTA cluster (one TPC) per 256 x BN tile: tcgen05.mma.cta_group::2 (M=256) issued by the
+//    leader CTA; each CTA stages its own 128 A rows and HALF of the B tile, so B's L2->SMEM traffic and
+//    shared-memory fill per SM halve.  TMA of both CTAs signals the leader's "full" barrier; tcgen05.commit
+//    multicasts "slot free" / "accumulator ready" to both CTAs; epilogue warps of both CTAs release the
+//    accumulator on the leader's barrier.
 //  * Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue
-//    (warp w reads TMEM lanes 32*(w%4).. : thread <-> output row).
+//    (warp w reads TMEM lanes 32*(w%4).. : thread <-> output row), then transposes 32x32 fp32 blocks
+//    through a padded shared-memory staging tile so that every global access is row-contiguous
+//    (8 lanes x 16 B = one full 128 B line per row).
+//  * Tiles are rasterised in groups of `group_m` m-tiles that sweep n: the A panel of a group stays in L2.
 //  * Epilogues (fused, no extra pass over HBM):
 //      EPI_AFFINE : v = (acc + bias[n]) * gate[row/gate_div, n] * alpha + res[row, n]
 //                   -> fp32 and/or bf16 and/or Snake(v) bf16   (DiT residual/gate, ODE axpy, codec convs)
@@ -35,9 +44,10 @@ struct GemmParams {
   // tiling
   int rows_per_item;    // T: rows per batch item (tiles never straddle items)
   int n_items;
-  int tiles_per_item;   // ceil(T / 128)
+  int tiles_per_item;   // ceil(T / (128 * CG))  — "unit" tiles (a CTA for CG=1, a CTA pair for CG=2)
   int N;                // valid output columns
   int n_tiles_n;
+  int group_m;          // rasterisation: unit m-tiles per L2-resident A panel
   // K loop
   int n_runs[2];
   KRun runs[2][GEMM_MAX_RUNS];
@@ -56,27 +66,102 @@ struct GemmParams {
   const float2* rope; int rope_T; int use_rope; float eps;
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int CG>
 struct GemmSmem {
   static constexpr int kABytes = GEMM_BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStageLd = 36;                          // fp32 words per staged row (32 + 4 pad)
+  static constexpr int kEpiBytes = 4 * 32 * kStageLd * 4;      // 4 epilogue warps x 32 rows
   static constexpr int kBarBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int kBudget = 227 * 1024 - kEpiBytes - kBarBytes - 1024;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: manual alignment
 };
 
-template <int BN, int BK, int MODE>
+// ---- cluster helpers (CG = 2) ----
+SAB_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SAB_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+SAB_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: address of the leader CTA's barrier
+SAB_DEVICE void tma_load_2d_cg2(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+SAB_DEVICE void tma_load_3d_cg2(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+SAB_DEVICE void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+SAB_DEVICE void umma_commit_cg2(uint64_t* bar) {  // arrive on `bar` in both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+template <int kCols>
+SAB_DEVICE void tmem_alloc_cg2(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+SAB_DEVICE void tmem_dealloc_cg2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// tile -> (unit m-tile, n-tile): groups of `group_m` m-tiles sweep n (m fastest inside a group)
+SAB_DEVICE void tile_coords(int tile, int n_tiles_m, int n_tiles_n, int group_m, int& mt, int& nt) {
+  const int per_group = group_m * n_tiles_n;
+  const int g = tile / per_group;
+  const int idx = tile - g * per_group;
+  const int m_first = g * group_m;
+  const int gsz = (n_tiles_m - m_first < group_m) ? (n_tiles_m - m_first) : group_m;
+  nt = idx / gsz;
+  mt = m_first + (idx - nt * gsz);
+}
+
+SAB_DEVICE uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
+
+template <int BN, int BK, int MODE, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams P) {
-  using S = GemmSmem<BN, BK>;
+  using S = GemmSmem<BN, BK, CG>;
   constexpr int kStages = S::kStages;
+  constexpr int kLd = S::kStageLd;
   constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr int kAccStride = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;  // column offset of accumulator 1
   static_assert(2 * kAccStride <= 512, "accumulators exceed TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
   static_assert(BK == 64 || BK == 32, "BK must be one swizzle row (128B or 64B)");
+  static_assert(CG == 1 || CG == 2, "cta group");
+  static_assert(kStages >= 2, "pipeline too shallow");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,9 +171,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(bar_base + S::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
   const int n_tiles_m = P.n_items * P.tiles_per_item;
   const int n_tiles = n_tiles_m * P.n_tiles_n;
 
@@ -103,26 +192,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], 4 * CG);  // one arrive per epilogue warp of every CTA of the group
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_cg2<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mt = tile % n_tiles_m, nt = tile / n_tiles_m;
+      for (int tile = unit; tile < n_tiles; tile += n_units) {
+        int mt, nt;
+        tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
         const int item = mt / P.tiles_per_item;
-        const int t0 = (mt % P.tiles_per_item) * GEMM_BM;
+        const int t0 = (mt % P.tiles_per_item) * (GEMM_BM * CG) + (int)cta_rank * GEMM_BM;
         const int n0 = nt * BN;
+        const int nb = n0 + (int)cta_rank * (BN / CG);   // this CTA's slice of the B tile
         const int list = (P.n_period > 0 && (n0 % P.n_period) >= P.n_switch) ? 1 : 0;
         int kb_global = 0;
         for (int r = 0; r < P.n_runs[list]; ++r) {
@@ -131,24 +225,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * S::kStageBytes;
             uint8_t* sb = sa + S::kABytes;
-            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_3d(sa, &tmA, &full_bar[stage], run.a_col + kb * BK, t0 + run.row_shift, item);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb_global * BK, n0);
+            if constexpr (CG == 2) {
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+              tma_load_3d_cg2(sa, &tmA, &full_bar[stage], run.a_col + kb * BK, t0 + run.row_shift, item);
+              tma_load_2d_cg2(sb, &tmB, &full_bar[stage], kb_global * BK, nb);
+            } else {
+              mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+              tma_load_3d(sa, &tmA, &full_bar[stage], run.a_col + kb * BK, t0 + run.row_shift, item);
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb_global * BK, nb);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nt = tile / n_tiles_m;
+      for (int tile = unit; tile < n_tiles; tile += n_units) {
+        int mt, nt;
+        tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
         const int n0 = nt * BN;
         const int list = (P.n_period > 0 && (n0 % P.n_period) >= P.n_switch) ? 1 : 0;
         int total_kb = 0;
@@ -166,95 +267,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_cg2(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            else umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (CG == 2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter
+    // ===================== epilogue (every CTA) =====================
+    const int q = warp & 3;                    // TMEM lane quarter
+    float* stg = epi_stage + q * 32 * kLd;     // this warp's staging tile
+    const int tr_r = lane >> 3;                // transposed mapping: pass p covers rows 4p + tr_r,
+    const int tr_c = (lane & 7) * 4;           //   4 consecutive columns tr_c .. tr_c+3
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int mt = tile % n_tiles_m, nt = tile / n_tiles_m;
+    for (int tile = unit; tile < n_tiles; tile += n_units) {
+      int mt, nt;
+      tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
       const int item = mt / P.tiles_per_item;
-      const int t_in_item = (mt % P.tiles_per_item) * GEMM_BM + q * 32 + lane;
-      const bool row_ok = t_in_item < P.rows_per_item;
-      const long long row = (long long)item * P.rows_per_item + t_in_item;
+      const int t_base = (mt % P.tiles_per_item) * (GEMM_BM * CG) + (int)cta_rank * GEMM_BM + q * 32;  // row of lane 0
+      const long long row_base = (long long)item * P.rows_per_item + t_base;
+      const int rows_left = P.rows_per_item - t_base;   // rows r < rows_left are valid
       const int n0 = nt * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      if constexpr (MODE != EPI_AFFINE) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+      }
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
+      // write this thread's 32 accumulator values (one row) into the staging tile, then read them back transposed
+      auto stage_put = [&](const float (&v)[32]) {
+        float4* dst = reinterpret_cast<float4*>(stg + lane * kLd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+      };
+      auto stage_get = [&](int p) { return *reinterpret_cast<const float4*>(stg + (4 * p + tr_r) * kLd + tr_c); };
+
       if constexpr (MODE == EPI_AFFINE) {
-        const float* gate_row = P.gate ? P.gate + (long long)(row / P.gate_div) * P.gate_ld : nullptr;
+        // Side inputs (fp32 residual, adaLN gate) are fetched one chunk ahead into registers: 8 independent 16 B
+        // loads per lane are in flight while the previous chunk is transposed and stored, and the first chunk's
+        // loads are issued before waiting for the accumulator.
+        float4 rr[8], gg[8], rr_n[8], gg_n[8];
+        auto load_side = [&](int c, float4 (&r4)[8], float4 (&g4)[8]) {
+          const int n = n0 + c + tr_c;
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const int r = 4 * p + tr_r;
+            r4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[p] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (r < rows_left && n0 + c < P.N) {
+              const long long row = row_base + r;
+              if (P.res) r4[p] = *reinterpret_cast<const float4*>(P.res + row * P.res_ld + n);
+              if (P.gate) g4[p] = __ldg(reinterpret_cast<const float4*>(P.gate + (row / P.gate_div) * P.gate_ld + n));
+            }
+          }
+        };
+        load_side(0, rr, gg);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= P.N) break;
+          if (c + 32 < BN) load_side(c + 32, rr_n, gg_n);
           float v[32];
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
-          const int n = n0 + c;
-          if (row_ok && n < P.N) {
-            if (P.bias) {
-              const int nb = P.bias_mod ? (n % P.bias_mod) : n;
+          stage_put(v);
+          const int n = n0 + c + tr_c;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4;
+          const int nm = P.bias_mod ? (n % P.bias_mod) : n;
+          if (P.bias) bias4 = __ldg(reinterpret_cast<const float4*>(P.bias + nm));
+          if (P.out_act) sa4 = __ldg(reinterpret_cast<const float4*>(P.snake_alpha + nm));
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(P.bias + nb + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          for (int p = 0; p < 8; ++p) {
+            const int r = 4 * p + tr_r;
+            if (r < rows_left) {
+              const long long row = row_base + r;
+              float4 x = stage_get(p);
+              const float4 g = gg[p], rsd = rr[p];
+              x.x = (x.x + bias4.x) * g.x * P.alpha + rsd.x;
+              x.y = (x.y + bias4.y) * g.y * P.alpha + rsd.y;
+              x.z = (x.z + bias4.z) * g.z * P.alpha + rsd.z;
+              x.w = (x.w + bias4.w) * g.w * P.alpha + rsd.w;
+              if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + n) = x;
+              if (P.out_bf16) *reinterpret_cast<uint2*>(P.out_bf16 + row * P.out_bf16_ld + n) = pack4_bf16(x);
+              if (P.out_act) {
+                float s;
+                s = __sinf(sa4.x * x.x); x.x += s * s * __frcp_rn(sa4.x + 1e-9f);
+                s = __sinf(sa4.y * x.y); x.y += s * s * __frcp_rn(sa4.y + 1e-9f);
+                s = __sinf(sa4.z * x.z); x.z += s * s * __frcp_rn(sa4.z + 1e-9f);
+                s = __sinf(sa4.w * x.w); x.w += s * s * __frcp_rn(sa4.w + 1e-9f);
+                *reinterpret_cast<uint2*>(P.out_act + row * P.out_act_ld + n) = pack4_bf16(x);
               }
-            }
-            if (gate_row) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 g = *reinterpret_cast<const float4*>(gate_row + n + j);
-                v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-              }
-            }
-            if (P.alpha != 1.f) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= P.alpha;
-            }
-            if (P.res) {
-              const float* rp = P.res + row * P.res_ld + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
-              }
-            }
-            if (P.out_f32) {
-              float* op = P.out_f32 + row * P.out_f32_ld + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (P.out_bf16) {
-              uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + row * P.out_bf16_ld + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-            }
-            if (P.out_act) {
-              const int na = P.bias_mod ? (n % P.bias_mod) : n;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float a = P.snake_alpha[na + j];
-                const float s = __sinf(a * v[j]);
-                v[j] += s * s * __frcp_rn(a + 1e-9f);
-              }
-              uint4* op = reinterpret_cast<uint4*>(P.out_act + row * P.out_act_ld + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             }
           }
+#pragma unroll
+          for (int p = 0; p < 8; ++p) { rr[p] = rr_n[p]; gg[p] = gg_n[p]; }
+          __syncwarp();  // staging tile is rewritten by the next chunk
         }
       } else if constexpr (MODE == EPI_SWIGLU) {
         // tile columns: [32 gate | 32 up] pairs -> BN/2 outputs at column n0/2
@@ -264,24 +378,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(t_addr + c, g);
           tmem_ld32(t_addr + c + 32, u);
           tmem_ld_wait();
-          const int n_out = (n0 + c) >> 1;
-          if (row_ok && (n0 + c) < P.N) {
+          if (n0 + c >= P.N) break;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g[j] = silu_f(g[j]) * u[j];
-            uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + row * P.out_bf16_ld + n_out);
+          for (int j = 0; j < 32; ++j) g[j] = silu_f(g[j]) * u[j];
+          stage_put(g);
+          const int n = ((n0 + c) >> 1) + tr_c;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              op[j] = make_uint4(pack_bf16(g[8 * j], g[8 * j + 1]), pack_bf16(g[8 * j + 2], g[8 * j + 3]),
-                                 pack_bf16(g[8 * j + 4], g[8 * j + 5]), pack_bf16(g[8 * j + 6], g[8 * j + 7]));
+          for (int p = 0; p < 8; ++p) {
+            const int r = 4 * p + tr_r;
+            if (r < rows_left)
+              *reinterpret_cast<uint2*>(P.out_bf16 + (row_base + r) * P.out_bf16_ld + n) = pack4_bf16(stage_get(p));
           }
+          __syncwarp();
         }
       } else {  // EPI_QKV: BN is a multiple of 128; each 128-col group is one head
-        const int pos = (int)(row % P.rope_T);
 #pragma unroll 1
         for (int hc = 0; hc < BN; hc += 128) {
-          const int n = n0 + hc;
-          const float* nw = (n < P.n_q_end) ? P.qnorm_w : (n < P.n_k_end ? P.knorm_w : nullptr);
-          float rstd = 1.f;
+          const int nh = n0 + hc;
+          if (nh >= P.N) break;
+          const float* nw = (nh < P.n_q_end) ? P.qnorm_w : (nh < P.n_k_end ? P.knorm_w : nullptr);
+          float rstd = 1.f;   // of this thread's row (lane = row)
           if (nw) {
             float ss = 0.f;
 #pragma unroll 1
@@ -299,43 +415,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[32];
             tmem_ld32(t_addr + hc + c, v);
             tmem_ld_wait();
-            if (row_ok && n < P.N) {
-              if (nw) {
+            stage_put(v);
+            const int cc = c + tr_c;              // column inside the head
+            float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (nw) w4 = __ldg(reinterpret_cast<const float4*>(nw + cc));
+            float4 cs4[8];
+            if (nw && P.use_rope) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * nw[c + j];
-                if (P.use_rope) {
-                  const float2* rp = P.rope + (long long)pos * 64 + (c >> 1);
+              for (int p = 0; p < 8; ++p) {
+                const int pos = (int)((row_base + 4 * p + tr_r) % P.rope_T);
+                cs4[p] = __ldg(reinterpret_cast<const float4*>(P.rope + (long long)pos * 64 + (cc >> 1)));
+              }
+            }
 #pragma unroll
-                  for (int j = 0; j < 32; j += 2) {
-                    const float2 cs = rp[j >> 1];
-                    const float x0 = v[j], x1 = v[j + 1];
-                    v[j] = x0 * cs.x - x1 * cs.y;
-                    v[j + 1] = x0 * cs.y + x1 * cs.x;
+            for (int p = 0; p < 8; ++p) {
+              const int r = 4 * p + tr_r;
+              const float rs = __shfl_sync(0xffffffffu, rstd, r);
+              if (r < rows_left) {
+                const long long row = row_base + r;
+                float4 x = stage_get(p);
+                if (nw) {
+                  x.x *= rs * w4.x; x.y *= rs * w4.y; x.z *= rs * w4.z; x.w *= rs * w4.w;
+                  if (P.use_rope) {
+                    const float4 cs = cs4[p];
+                    const float a0 = x.x * cs.x - x.y * cs.y, a1 = x.x * cs.y + x.y * cs.x;
+                    const float b0 = x.z * cs.z - x.w * cs.w, b1 = x.z * cs.w + x.w * cs.z;
+                    x = make_float4(a0, a1, b0, b1);
                   }
                 }
+                *reinterpret_cast<uint2*>(P.out_bf16 + row * P.out_bf16_ld + nh + cc) = pack4_bf16(x);
               }
-              uint4* op = reinterpret_cast<uint4*>(P.out_bf16 + row * P.out_bf16_ld + n + c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
             }
+            __syncwarp();
           }
         }
       }
-      // release the accumulator back to the MMA warp
+      // release the accumulator back to the MMA warp (on the leader CTA's barrier)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 

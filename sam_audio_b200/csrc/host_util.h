@@ -124,7 +124,7 @@ inline CUtensorMap make_tmap_2d(const void* base, int64_t cols, int64_t rows, in
 struct GemmOp {
   CUtensorMap tmA, tmB;
   GemmParams P;
-  int BN = 0, BK = 64, mode = EPI_AFFINE;
+  int BN = 0, BK = 64, mode = EPI_AFFINE, cg = 1;
   int grid = 0;
   const char* tag = "";
   double flops = 0;  // algorithmic 2*M*N*K

@@ -29,16 +29,19 @@ def capi():
     return _capi
 
 
-@pytest.mark.parametrize("M,N,K,bn,bk", [
-    (128, 256, 64, 256, 64), (300, 256, 256, 256, 64), (1000, 512, 2048, 128, 64), (2500, 2048, 2048, 256, 64),
-    (300, 96, 96, 96, 32), (777, 128, 160, 128, 32), (500, 192, 192, 192, 64), (333, 96, 192, 96, 64),
-    (129, 64, 128, 64, 64), (1, 256, 64, 256, 64)])
-def test_tcgen05_gemm(capi, M, N, K, bn, bk):
+@pytest.mark.parametrize("M,N,K,bn,bk,cg", [
+    (128, 256, 64, 256, 64, 1), (300, 256, 256, 256, 64, 1), (1000, 512, 2048, 128, 64, 1),
+    (2500, 2048, 2048, 256, 64, 1), (300, 96, 96, 96, 32, 1), (777, 128, 160, 128, 32, 1),
+    (500, 192, 192, 192, 64, 1), (333, 96, 192, 96, 64, 1), (129, 64, 128, 64, 64, 1), (1, 256, 64, 256, 64, 1),
+    # cta_group::2 pairs (256-row tiles)
+    (256, 256, 64, 256, 64, 2), (300, 512, 256, 256, 64, 2), (2500, 2048, 2048, 256, 64, 2),
+    (16000, 2816, 2816, 256, 64, 2), (100, 256, 128, 256, 64, 2), (5000, 11008, 512, 256, 64, 0)])
+def test_tcgen05_gemm(capi, M, N, K, bn, bk, cg):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
     c = torch.full((M, N), float("nan"), device="cuda")
-    capi.check(capi.lib().sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), bn, bk, capi.stream_ptr()))
+    capi.check(capi.lib().sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), bn, bk, cg, capi.stream_ptr()))
     torch.cuda.synchronize()
     assert not torch.isnan(c).any()
     assert rel_l2(c, a.float() @ b.float().t()) < 1e-3

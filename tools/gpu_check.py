@@ -24,21 +24,23 @@ def rel(a, b):
 def stage_gemm():
     L = _capi.lib()
     ok = True
-    for (M, N, K, bn, bk) in [(128, 256, 64, 256, 64), (128, 128, 64, 128, 64), (300, 256, 256, 256, 64),
-                              (1000, 512, 2048, 256, 64), (1000, 512, 2048, 128, 64), (4096, 4096, 4096, 256, 64),
-                              (300, 96, 96, 96, 32), (777, 128, 160, 128, 32), (500, 192, 192, 192, 64),
-                              (333, 96, 192, 96, 64), (129, 64, 128, 64, 64)]:
+    for (M, N, K, bn, bk, cg) in [(128, 256, 64, 256, 64, 1), (128, 128, 64, 128, 64, 1), (300, 256, 256, 256, 64, 1),
+                                  (1000, 512, 2048, 256, 64, 1), (4096, 4096, 4096, 256, 64, 1),
+                                  (300, 96, 96, 96, 32, 1), (777, 128, 160, 128, 32, 1), (500, 192, 192, 192, 64, 1),
+                                  (333, 96, 192, 96, 64, 1), (129, 64, 128, 64, 64, 1),
+                                  (256, 256, 64, 256, 64, 2), (300, 512, 256, 256, 64, 2), (1000, 512, 2048, 256, 64, 2),
+                                  (4096, 4096, 4096, 256, 64, 2), (16000, 2816, 2816, 256, 64, 2)]:
         g = torch.Generator(device="cuda").manual_seed(M + N + K)
         a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
         b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
         c = torch.full((M, N), float("nan"), device="cuda")
-        _capi.check(L.sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), bn, bk, _capi.stream_ptr()))
+        _capi.check(L.sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), bn, bk, cg, _capi.stream_ptr()))
         torch.cuda.synchronize()
         ref = a.float() @ b.float().t()
         e = rel(c, ref)
         good = e < 1e-3 and not torch.isnan(c).any()
         ok &= bool(good)
-        print(f"gemm M={M} N={N} K={K} BN={bn} BK={bk}: rel={e:.3e} nan={int(torch.isnan(c).sum())} {'OK' if good else 'FAIL'}",
+        print(f"gemm M={M} N={N} K={K} BN={bn} BK={bk} CG={cg}: rel={e:.3e} nan={int(torch.isnan(c).sum())} {'OK' if good else 'FAIL'}",
               flush=True)
         if not good:
             d = (c - ref).abs()
@@ -49,17 +51,21 @@ def stage_gemm():
     a = torch.randn(M, K, device="cuda").bfloat16()
     b = torch.randn(N, K, device="cuda").bfloat16()
     c = torch.empty(M, N, device="cuda")
-    for _ in range(2):
-        _capi.check(L.sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), 256, 64, _capi.stream_ptr()))
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        _capi.check(L.sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), 256, 64, _capi.stream_ptr()))
-    e1.record()
+    for cg in (1, 2):
+        for _ in range(2):
+            _capi.check(L.sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), 256, 64, cg, _capi.stream_ptr()))
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            _capi.check(L.sab_test_gemm(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), 256, 64, cg, _capi.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"gemm 8192^3 BN=256 CG={cg}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for _ in range(2):
+        torch.matmul(a, b.t())
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    print(f"gemm 8192^3 BN=256: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
     e0.record()
     for _ in range(5):
         torch.matmul(a, b.t())
