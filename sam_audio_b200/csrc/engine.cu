@@ -730,6 +730,8 @@ struct CodecStep {
   GemmOp op;
 };
 struct CodecPlan {
+  std::vector<std::unique_ptr<std::string>> tags;   // owned tag strings (profiling labels)
+  const char* tag(const std::string& t) { tags.push_back(std::make_unique<std::string>(t)); return tags.back()->c_str(); }
   int items = 0;       // waveforms per chunk
   long long S = 0;     // samples per waveform
   DevicePool pool;
@@ -766,7 +768,7 @@ static void plan_resunit(CodecPlan& cp, const ResUnitW& R, int items, long long 
     RunList rl;
     for (int k = 0; k < 7; ++k) rl.add(0, (k - 3) * R.c7.dil, 0, C / bk);
     CodecStep s;
-    s.op = make_gemm("codec.res.conv7", seq_view(sb.a, items, Tn, C), R.c7.w, C, bn, bk, EPI_AFFINE, rl);
+    s.op = make_gemm(cp.tag(fmt("codec.res.conv7.c%d", C)), seq_view(sb.a, items, Tn, C), R.c7.w, C, bn, bk, EPI_AFFINE, rl);
     s.op.P.bias = R.c7.bias;
     s.op.P.out_act = sb.mid; s.op.P.out_act_ld = C; s.op.P.snake_alpha = R.a1;
     cp.flops += s.op.flops;
@@ -776,7 +778,7 @@ static void plan_resunit(CodecPlan& cp, const ResUnitW& R, int items, long long 
     RunList rl;
     rl.add(0, 0, 0, C / bk);
     CodecStep s;
-    s.op = make_gemm("codec.res.conv1", seq_view(sb.mid, items, Tn, C), R.c1.w, C, bn, bk, EPI_AFFINE, rl);
+    s.op = make_gemm(cp.tag(fmt("codec.res.conv1.c%d", C)), seq_view(sb.mid, items, Tn, C), R.c1.w, C, bn, bk, EPI_AFFINE, rl);
     s.op.P.bias = R.c1.bias;
     s.op.P.res = sb.x; s.op.P.res_ld = C;
     if (keep_x) { s.op.P.out_f32 = sb.x; s.op.P.out_f32_ld = C; }
@@ -818,7 +820,7 @@ static CodecPlan* get_enc_plan(sab_engine* e, int items, long long S) {
     rl.add(0, +1, 0, (s - pd) * C / bk);
     CodecStep st;
     AView av{sb.a, (int64_t)s * C, To, items, (int64_t)s * C, To * s * C};
-    st.op = make_gemm("codec.enc.down", av, B.down.w, C2, pick_bn(C2), bk, EPI_AFFINE, rl);
+    st.op = make_gemm(cp.tag(fmt("codec.enc.down.c%d", C)), av, B.down.w, C2, pick_bn(C2), bk, EPI_AFFINE, rl);
     st.op.P.bias = B.down.bias;
     const bool last = (i == c.codec_n_rates - 1);
     st.op.P.out_f32 = nb.x; st.op.P.out_f32_ld = C2;
@@ -906,7 +908,7 @@ static CodecPlan* get_dec_plan(sab_engine* e, int items, long long T) {
       rl.add(0, 0, 0, C / bk); rl.add(0, -1, 0, C / bk);
       rl.add(1, 0, 0, C / bk); rl.add(1, +1, 0, C / bk);
       CodecStep st;
-      st.op = make_gemm("codec.dec.up", seq_view(a_cur, items, Tn, C), B.up.w, s * Co, bn, bk, EPI_AFFINE, rl);
+      st.op = make_gemm(cp.tag(fmt("codec.dec.up.c%d", C)), seq_view(a_cur, items, Tn, C), B.up.w, s * Co, bn, bk, EPI_AFFINE, rl);
       st.op.P.bias = B.up.bias; st.op.P.bias_mod = Co;
       st.op.P.out_f32 = sb.x; st.op.P.out_f32_ld = (long long)s * Co;
       st.op.P.out_act = sb.a; st.op.P.out_act_ld = (long long)s * Co; st.op.P.snake_alpha = B.ru[0].a0;

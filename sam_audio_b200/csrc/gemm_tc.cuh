@@ -13,7 +13,8 @@
 //    shared-memory fill per SM halve.  TMA of both CTAs signals the leader's "full" barrier; tcgen05.commit
 //    multicasts "slot free" / "accumulator ready" to both CTAs; epilogue warps of both CTAs release the
 //    accumulator on the leader's barrier.
-//  * Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue
+//  * Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue, two warps per
+//    TMEM lane quarter taking alternating 32-column chunks
 //    (warp w reads TMEM lanes 32*(w%4).. : thread <-> output row), then transposes 32x32 fp32 blocks
 //    through a padded shared-memory staging tile so that every global access is row-contiguous
 //    (8 lanes x 16 B = one full 128 B line per row).
@@ -29,7 +30,7 @@
 namespace sab {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // 4 role warps + 8 epilogue warps
 constexpr int GEMM_MAX_RUNS = 8;
 
 enum EpiMode { EPI_AFFINE = 0, EPI_SWIGLU = 1, EPI_QKV = 2 };
@@ -72,7 +73,7 @@ struct GemmSmem {
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStageLd = 36;                          // fp32 words per staged row (32 + 4 pad)
-  static constexpr int kEpiBytes = 4 * 32 * kStageLd * 4;      // 4 epilogue warps x 32 rows
+  static constexpr int kEpiBytes = 8 * 32 * kStageLd * 4;      // 8 epilogue warps x 32 rows
   static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 227 * 1024 - kEpiBytes - kBarBytes - 1024;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
@@ -192,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * CG);  // one arrive per epilogue warp of every CTA of the group
+      mbar_init(&tmem_empty[a], 8 * CG);  // one arrive per epilogue warp of every CTA of the group
     }
     fence_barrier_init();
   }
@@ -278,10 +279,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (every CTA) =====================
-    const int q = warp & 3;                    // TMEM lane quarter
-    float* stg = epi_stage + q * 32 * kLd;     // this warp's staging tile
-    const int tr_r = lane >> 3;                // transposed mapping: pass p covers rows 4p + tr_r,
+    // ===================== epilogue (every CTA): 8 warps, 2 per TMEM lane quarter =====================
+    // Two warps share each SM sub-partition so one can issue while the other waits on TMEM / shared / global
+    // latency; every inner loop is straight-line (8 independent rows per lane) so the compiler can overlap them.
+    const int e = warp - 4;                    // 0..7
+    const int q = e & 3;                       // TMEM lane quarter (== warp % 4)
+    const int half = e >> 2;                   // which alternating 32-column chunks this warp owns
+    float* stg = epi_stage + e * 32 * kLd;     // this warp's staging tile
+    const int tr_r = lane >> 3;                // transposed mapping: pass p covers row 4p + tr_r,
     const int tr_c = (lane & 7) * 4;           //   4 consecutive columns tr_c .. tr_c+3
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -290,13 +295,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
       const int item = mt / P.tiles_per_item;
       const int t_base = (mt % P.tiles_per_item) * (GEMM_BM * CG) + (int)cta_rank * GEMM_BM + q * 32;  // row of lane 0
-      const long long row_base = (long long)item * P.rows_per_item + t_base;
-      const int rows_left = P.rows_per_item - t_base;   // rows r < rows_left are valid
+      const long long row0 = (long long)item * P.rows_per_item + t_base + tr_r;   // this lane's row in pass 0
+      const int rl = P.rows_per_item - t_base - tr_r;   // pass p is valid iff 4p < rl
       const int n0 = nt * BN;
-      if constexpr (MODE != EPI_AFFINE) {
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-      }
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
       // write this thread's 32 accumulator values (one row) into the staging tile, then read them back transposed
@@ -306,94 +307,121 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
       };
-      auto stage_get = [&](int p) { return *reinterpret_cast<const float4*>(stg + (4 * p + tr_r) * kLd + tr_c); };
+      auto stage_get = [&](float4 (&x)[8]) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) x[p] = *reinterpret_cast<const float4*>(stg + (4 * p + tr_r) * kLd + tr_c);
+      };
 
       if constexpr (MODE == EPI_AFFINE) {
-        // Side inputs (fp32 residual, adaLN gate) are fetched one chunk ahead into registers: 8 independent 16 B
-        // loads per lane are in flight while the previous chunk is transposed and stored, and the first chunk's
-        // loads are issued before waiting for the accumulator.
-        float4 rr[8], gg[8], rr_n[8], gg_n[8];
-        auto load_side = [&](int c, float4 (&r4)[8], float4 (&g4)[8]) {
-          const int n = n0 + c + tr_c;
+        // fp32 residual rows are fetched one chunk ahead (8 independent 16 B loads per lane in flight while the
+        // previous chunk is transposed and stored); the first chunk's loads go out before the accumulator wait.
+        const float* res0 = P.res ? P.res + row0 * P.res_ld + n0 + tr_c : nullptr;
+        const long long res_step = 4 * P.res_ld;
+        float4 rr[8], rr_n[8];
+        auto load_res = [&](int c, float4 (&r4)[8]) {
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
-            const int r = 4 * p + tr_r;
             r4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            g4[p] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (r < rows_left && n0 + c < P.N) {
-              const long long row = row_base + r;
-              if (P.res) r4[p] = *reinterpret_cast<const float4*>(P.res + row * P.res_ld + n);
-              if (P.gate) g4[p] = __ldg(reinterpret_cast<const float4*>(P.gate + (row / P.gate_div) * P.gate_ld + n));
-            }
+            if (res0 && 4 * p < rl && n0 + c < P.N) r4[p] = *reinterpret_cast<const float4*>(res0 + p * res_step + c);
           }
         };
-        load_side(0, rr, gg);
+        load_res(half * 32, rr);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * 32; c < BN; c += 64) {
           if (n0 + c >= P.N) break;
-          if (c + 32 < BN) load_side(c + 32, rr_n, gg_n);
+          if (c + 64 < BN) load_res(c + 64, rr_n);
           float v[32];
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
           stage_put(v);
           const int n = n0 + c + tr_c;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4;
-          const int nm = P.bias_mod ? (n % P.bias_mod) : n;
-          if (P.bias) bias4 = __ldg(reinterpret_cast<const float4*>(P.bias + nm));
-          if (P.out_act) sa4 = __ldg(reinterpret_cast<const float4*>(P.snake_alpha + nm));
+          float4 x[8];
+          stage_get(x);
+          if (P.bias) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + (P.bias_mod ? (n % P.bias_mod) : n)));
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const int r = 4 * p + tr_r;
-            if (r < rows_left) {
-              const long long row = row_base + r;
-              float4 x = stage_get(p);
-              const float4 g = gg[p], rsd = rr[p];
-              x.x = (x.x + bias4.x) * g.x * P.alpha + rsd.x;
-              x.y = (x.y + bias4.y) * g.y * P.alpha + rsd.y;
-              x.z = (x.z + bias4.z) * g.z * P.alpha + rsd.z;
-              x.w = (x.w + bias4.w) * g.w * P.alpha + rsd.w;
-              if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + n) = x;
-              if (P.out_bf16) *reinterpret_cast<uint2*>(P.out_bf16 + row * P.out_bf16_ld + n) = pack4_bf16(x);
-              if (P.out_act) {
-                float s;
-                s = __sinf(sa4.x * x.x); x.x += s * s * __frcp_rn(sa4.x + 1e-9f);
-                s = __sinf(sa4.y * x.y); x.y += s * s * __frcp_rn(sa4.y + 1e-9f);
-                s = __sinf(sa4.z * x.z); x.z += s * s * __frcp_rn(sa4.z + 1e-9f);
-                s = __sinf(sa4.w * x.w); x.w += s * s * __frcp_rn(sa4.w + 1e-9f);
-                *reinterpret_cast<uint2*>(P.out_act + row * P.out_act_ld + n) = pack4_bf16(x);
-              }
+            for (int p = 0; p < 8; ++p) { x[p].x += b4.x; x[p].y += b4.y; x[p].z += b4.z; x[p].w += b4.w; }
+          }
+          if (P.gate) {
+            const float* g0 = P.gate + n;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const long long row = row0 + 4 * p;
+              const float4 g = __ldg(reinterpret_cast<const float4*>(g0 + ((4 * p < rl) ? (row / P.gate_div) : 0) * P.gate_ld));
+              x[p].x *= g.x; x[p].y *= g.y; x[p].z *= g.z; x[p].w *= g.w;
             }
           }
 #pragma unroll
-          for (int p = 0; p < 8; ++p) { rr[p] = rr_n[p]; gg[p] = gg_n[p]; }
+          for (int p = 0; p < 8; ++p) {
+            x[p].x = fmaf(x[p].x, P.alpha, rr[p].x); x[p].y = fmaf(x[p].y, P.alpha, rr[p].y);
+            x[p].z = fmaf(x[p].z, P.alpha, rr[p].z); x[p].w = fmaf(x[p].w, P.alpha, rr[p].w);
+          }
+          if (P.out_f32) {
+            float* o0 = P.out_f32 + row0 * P.out_f32_ld + n;
+            const long long st = 4 * P.out_f32_ld;
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+              if (4 * p < rl) *reinterpret_cast<float4*>(o0 + p * st) = x[p];
+          }
+          if (P.out_bf16) {
+            __nv_bfloat16* o0 = P.out_bf16 + row0 * P.out_bf16_ld + n;
+            const long long st = 4 * P.out_bf16_ld;
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+              if (4 * p < rl) *reinterpret_cast<uint2*>(o0 + p * st) = pack4_bf16(x[p]);
+          }
+          if (P.out_act) {   // Snake: v + sin^2(a v) / (a + 1e-9)
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.snake_alpha + (P.bias_mod ? (n % P.bias_mod) : n)));
+            const float4 i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
+            __nv_bfloat16* o0 = P.out_act + row0 * P.out_act_ld + n;
+            const long long st = 4 * P.out_act_ld;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              float s;
+              s = __sinf(a4.x * x[p].x); x[p].x = fmaf(s * s, i4.x, x[p].x);
+              s = __sinf(a4.y * x[p].y); x[p].y = fmaf(s * s, i4.y, x[p].y);
+              s = __sinf(a4.z * x[p].z); x[p].z = fmaf(s * s, i4.z, x[p].z);
+              s = __sinf(a4.w * x[p].w); x[p].w = fmaf(s * s, i4.w, x[p].w);
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+              if (4 * p < rl) *reinterpret_cast<uint2*>(o0 + p * st) = pack4_bf16(x[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < 8; ++p) rr[p] = rr_n[p];
           __syncwarp();  // staging tile is rewritten by the next chunk
         }
       } else if constexpr (MODE == EPI_SWIGLU) {
-        // tile columns: [32 gate | 32 up] pairs -> BN/2 outputs at column n0/2
+        // tile columns: [32 gate | 32 up] pairs -> BN/2 outputs at column n0/2; this warp owns alternating pairs
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = half * 64; c < BN; c += 128) {
+          if (n0 + c >= P.N) break;
           float g[32], u[32];
           tmem_ld32(t_addr + c, g);
           tmem_ld32(t_addr + c + 32, u);
           tmem_ld_wait();
-          if (n0 + c >= P.N) break;
 #pragma unroll
           for (int j = 0; j < 32; ++j) g[j] = silu_f(g[j]) * u[j];
           stage_put(g);
-          const int n = ((n0 + c) >> 1) + tr_c;
+          float4 x[8];
+          stage_get(x);
+          __nv_bfloat16* o0 = P.out_bf16 + row0 * P.out_bf16_ld + ((n0 + c) >> 1) + tr_c;
+          const long long st = 4 * P.out_bf16_ld;
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const int r = 4 * p + tr_r;
-            if (r < rows_left)
-              *reinterpret_cast<uint2*>(P.out_bf16 + (row_base + r) * P.out_bf16_ld + n) = pack4_bf16(stage_get(p));
-          }
+          for (int p = 0; p < 8; ++p)
+            if (4 * p < rl) *reinterpret_cast<uint2*>(o0 + p * st) = pack4_bf16(x[p]);
           __syncwarp();
         }
-      } else {  // EPI_QKV: BN is a multiple of 128; each 128-col group is one head
+      } else {  // EPI_QKV: each 128-col group is one head; this warp owns heads half, half+2, ... (BN=256: one each)
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        constexpr int kHeadStep = (BN >= 256) ? 256 : 128;   // BN=128: both warps of a quarter share the single head
 #pragma unroll 1
-        for (int hc = 0; hc < BN; hc += 128) {
+        for (int hc = (BN >= 256 ? half * 128 : 0); hc < BN; hc += kHeadStep) {
           const int nh = n0 + hc;
           if (nh >= P.N) break;
           const float* nw = (nh < P.n_q_end) ? P.qnorm_w : (nh < P.n_k_end ? P.knorm_w : nullptr);
@@ -410,42 +438,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             rstd = rsqrtf(ss * (1.f / 128.f) + P.eps);
           }
+          float rs[8];
+#pragma unroll
+          for (int p = 0; p < 8; ++p) rs[p] = __shfl_sync(0xffffffffu, rstd, 4 * p + tr_r);
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
+          for (int c = (BN >= 256 ? 0 : half * 32); c < 128; c += (BN >= 256 ? 32 : 64)) {
             float v[32];
             tmem_ld32(t_addr + hc + c, v);
             tmem_ld_wait();
             stage_put(v);
             const int cc = c + tr_c;              // column inside the head
-            float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (nw) w4 = __ldg(reinterpret_cast<const float4*>(nw + cc));
-            float4 cs4[8];
-            if (nw && P.use_rope) {
+            float4 x[8];
+            stage_get(x);
+            if (nw) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + cc));
 #pragma unroll
               for (int p = 0; p < 8; ++p) {
-                const int pos = (int)((row_base + 4 * p + tr_r) % P.rope_T);
-                cs4[p] = __ldg(reinterpret_cast<const float4*>(P.rope + (long long)pos * 64 + (cc >> 1)));
+                x[p].x *= rs[p] * w4.x; x[p].y *= rs[p] * w4.y; x[p].z *= rs[p] * w4.z; x[p].w *= rs[p] * w4.w;
               }
-            }
+              if (P.use_rope) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const int r = 4 * p + tr_r;
-              const float rs = __shfl_sync(0xffffffffu, rstd, r);
-              if (r < rows_left) {
-                const long long row = row_base + r;
-                float4 x = stage_get(p);
-                if (nw) {
-                  x.x *= rs * w4.x; x.y *= rs * w4.y; x.z *= rs * w4.z; x.w *= rs * w4.w;
-                  if (P.use_rope) {
-                    const float4 cs = cs4[p];
-                    const float a0 = x.x * cs.x - x.y * cs.y, a1 = x.x * cs.y + x.y * cs.x;
-                    const float b0 = x.z * cs.z - x.w * cs.w, b1 = x.z * cs.w + x.w * cs.z;
-                    x = make_float4(a0, a1, b0, b1);
-                  }
+                for (int p = 0; p < 8; ++p) {
+                  const int pos = (int)((row0 + 4 * p) % P.rope_T);
+                  const float4 cs = __ldg(reinterpret_cast<const float4*>(P.rope + (long long)pos * 64 + (cc >> 1)));
+                  const float a0 = x[p].x * cs.x - x[p].y * cs.y, a1 = x[p].x * cs.y + x[p].y * cs.x;
+                  const float b0 = x[p].z * cs.z - x[p].w * cs.w, b1 = x[p].z * cs.w + x[p].w * cs.z;
+                  x[p] = make_float4(a0, a1, b0, b1);
                 }
-                *reinterpret_cast<uint2*>(P.out_bf16 + row * P.out_bf16_ld + nh + cc) = pack4_bf16(x);
               }
             }
+            __nv_bfloat16* o0 = P.out_bf16 + row0 * P.out_bf16_ld + nh + cc;
+            const long long st = 4 * P.out_bf16_ld;
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+              if (4 * p < rl) *reinterpret_cast<uint2*>(o0 + p * st) = pack4_bf16(x[p]);
             __syncwarp();
           }
         }
