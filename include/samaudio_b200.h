@@ -116,6 +116,11 @@ int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, f
 int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, const void* k, const void* v,
                        const uint8_t* key_mask, void* o, void* stream);
 
+/* Same, through the tcgen05 self-attention kernel (Tq == Tk == T <= 256); v_lbo / v_sbo <= 0 select the
+ * defaults of the MN-major V descriptor. */
+int sab_test_attention_tc(int items, int heads, int T, const void* q, const void* k, const void* v,
+                          const uint8_t* key_mask, void* o, int v_lbo, int v_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

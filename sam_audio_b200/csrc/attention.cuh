@@ -206,4 +206,75 @@ attention_kernel(const AttnParams P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-attention to a handful of text tokens (Tk <= 16: "man speaking" is 3 tokens).  HBM-bound:
+// one warp per (query row, head); K/V of the (item, head) live in shared memory; each lane owns 4 of the
+// 128 head dims; scores by warp-shuffle reduction, softmax in registers.  Reads Q once, writes O once.
+// ---------------------------------------------------------------------------------------------
+constexpr int XATT_MAX_TK = 16, XATT_ROWS = 64, XATT_THREADS = 256;
+__global__ void __launch_bounds__(XATT_THREADS)
+xattn_small_kernel(const AttnParams P) {
+  __shared__ __align__(16) __nv_bfloat16 sK[XATT_MAX_TK][ATT_D];
+  __shared__ __align__(16) __nv_bfloat16 sV[XATT_MAX_TK][ATT_D];
+  __shared__ float sBias[XATT_MAX_TK];
+  const int qt = blockIdx.x, head = blockIdx.y, item = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* kb = P.k + (long long)item * P.Tk * P.k_ld + P.k_col0 + head * ATT_D;
+  const __nv_bfloat16* vb = P.v + (long long)item * P.Tk * P.v_ld + P.v_col0 + head * ATT_D;
+  for (int i = tid; i < P.Tk * (ATT_D / 8); i += XATT_THREADS) {   // 16 B per thread
+    const int j = i / (ATT_D / 8), c = (i % (ATT_D / 8)) * 8;
+    *reinterpret_cast<uint4*>(&sK[j][c]) = *reinterpret_cast<const uint4*>(kb + (long long)j * P.k_ld + c);
+    *reinterpret_cast<uint4*>(&sV[j][c]) = *reinterpret_cast<const uint4*>(vb + (long long)j * P.v_ld + c);
+  }
+  if (tid < P.Tk) sBias[tid] = (!P.key_mask || P.key_mask[(long long)item * P.Tk + tid]) ? 0.f : -INFINITY;
+  __syncthreads();
+  const __nv_bfloat16* qb = P.q + (long long)item * P.Tq * P.q_ld + P.q_col0 + head * ATT_D + lane * 4;
+  __nv_bfloat16* ob = P.o + (long long)item * P.Tq * P.o_ld + head * ATT_D + lane * 4;
+  const int r_end = min(P.Tq, (qt + 1) * XATT_ROWS);
+  constexpr int kRowsPerWarp = XATT_ROWS / (XATT_THREADS / 32);   // 8: all query loads are issued up front
+  uint2 qraw[kRowsPerWarp];
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int r = qt * XATT_ROWS + warp + i * (XATT_THREADS / 32);
+    qraw[i] = make_uint2(0u, 0u);
+    if (r < r_end) qraw[i] = *reinterpret_cast<const uint2*>(qb + (long long)r * P.q_ld);
+  }
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int r = qt * XATT_ROWS + warp + i * (XATT_THREADS / 32);
+    const float2 q01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[i].x));
+    const float2 q23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[i].y));
+    float sc[XATT_MAX_TK];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < XATT_MAX_TK; ++j) {
+      sc[j] = -INFINITY;
+      if (j < P.Tk) {
+        const uint2 kraw = *reinterpret_cast<const uint2*>(&sK[j][lane * 4]);
+        const float2 k01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kraw.x));
+        const float2 k23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kraw.y));
+        float d = q01.x * k01.x + q01.y * k01.y + q23.x * k23.x + q23.y * k23.y;
+        d = warp_sum(d);
+        sc[j] = d * P.scale_log2 + sBias[j];
+        mx = fmaxf(mx, sc[j]);
+      }
+    }
+    float den = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < XATT_MAX_TK; ++j) {
+      if (j < P.Tk) {
+        const float pj = exp2f(sc[j] - mx);
+        den += pj;
+        const uint2 vraw = *reinterpret_cast<const uint2*>(&sV[j][lane * 4]);
+        const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vraw.x));
+        const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vraw.y));
+        o0 = fmaf(pj, v01.x, o0); o1 = fmaf(pj, v01.y, o1); o2 = fmaf(pj, v23.x, o2); o3 = fmaf(pj, v23.y, o3);
+      }
+    }
+    const float inv = 1.f / den;
+    if (r < r_end)
+      *reinterpret_cast<uint2*>(ob + (long long)r * P.o_ld) = make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
+  }
+}
+
 }  // namespace sab

@@ -15,17 +15,18 @@ __global__ void __launch_bounds__(256)
 rmsnorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_ld, int rows_per_item,
                    __nv_bfloat16* __restrict__ out, int M, float eps) {
+  // Two streaming passes per row (the second one hits L1/L2): keeps the register count low enough for full
+  // occupancy, which is what hides HBM latency here (the single-pass, row-in-registers version ran at 8 warps/SM).
   constexpr int d = kVecPerLane * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
-  float4 v[kVecPerLane];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) {
-    v[i] = xr[lane + i * 32];
-    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    const float4 v = xr[lane + i * 32];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   ss = warp_sum(ss);
   const float rstd = rsqrtf(ss / (float)d + eps);
@@ -34,14 +35,15 @@ rmsnorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_ld);
   const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_ld);
   uint2* orow = reinterpret_cast<uint2*>(out + (long long)row * d);
-#pragma unroll
+#pragma unroll 2
   for (int i = 0; i < kVecPerLane; ++i) {
     const int c = lane + i * 32;
-    const float4 ww = wr[c], s1 = sc[c], s0 = sh[c];
-    const float a = v[i].x * rstd * ww.x * (1.f + s1.x) + s0.x;
-    const float bb = v[i].y * rstd * ww.y * (1.f + s1.y) + s0.y;
-    const float cc = v[i].z * rstd * ww.z * (1.f + s1.z) + s0.z;
-    const float dd = v[i].w * rstd * ww.w * (1.f + s1.w) + s0.w;
+    const float4 v = xr[c];
+    const float4 ww = __ldg(wr + c), s1 = __ldg(sc + c), s0 = __ldg(sh + c);
+    const float a = v.x * rstd * ww.x * (1.f + s1.x) + s0.x;
+    const float bb = v.y * rstd * ww.y * (1.f + s1.y) + s0.y;
+    const float cc = v.z * rstd * ww.z * (1.f + s1.z) + s0.z;
+    const float dd = v.w * rstd * ww.w * (1.f + s1.w) + s0.w;
     orow[c] = make_uint2(pack_bf16(a, bb), pack_bf16(cc, dd));
   }
 }

@@ -14,6 +14,7 @@
 #include "../../include/samaudio_b200.h"
 #include "host_util.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "elementwise.cuh"
 #include "codec_kernels.cuh"
 
@@ -506,6 +507,8 @@ struct DitPlan {
   // ops
   GemmOp g_t13, g_t2, g_tb, g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid;
   std::vector<LayerOps> lay;
+  CUtensorMap tm_att_q, tm_att_kv;   // fused-QKV buffer viewed as (3d cols, T rows, Bc items): box 64x128 / 64x256
+  bool att_tc = false;               // tcgen05 self-attention usable (T <= 256)
   double flops_per_eval = 0;
 };
 
@@ -600,6 +603,11 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
     o.w2.P.res = p.h; o.w2.P.res_ld = d; o.w2.P.out_f32 = p.h; o.w2.P.out_f32_ld = d;
   }
   p.g_out = make_linear("output", p.xn, M, d, e->w_out, c.out_channels, 256, EPI_AFFINE);
+  p.att_tc = (T <= 256) && !getenv("SAB_NO_TC_ATTENTION");
+  if (p.att_tc) {
+    p.tm_att_q = make_tmap_3d(p.qkv, 3LL * d, T, Bc, 3LL * d, (int64_t)T * 3 * d, 64, 128);
+    p.tm_att_kv = make_tmap_3d(p.qkv, 3LL * d, T, Bc, 3LL * d, (int64_t)T * 3 * d, 64, 256);
+  }
 
   // algorithmic FLOPs of one evaluation (GEMMs + attention), for roofline reporting
   double f = p.g_t13.flops + p.g_t2.flops + p.g_tb.flops + p.g_y13.flops + p.g_y2.flops + p.g_in.flops +
@@ -639,9 +647,28 @@ static void attention(sab_engine* e, const AttnParams& ap, int items, int heads,
     SAB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     configured = true;
   }
+  const double fl = 4.0 * items * heads * (double)ap.Tq * ap.Tk * 128;
+  if (ap.Tk <= XATT_MAX_TK && ap.k != ap.q) {   // a handful of text tokens: HBM-bound warp-per-row kernel
+    mark(e, st, "sdpa.cross", fl, (double)items * ap.Tq * heads * 128 * 4.0);
+    xattn_small_kernel<<<dim3((ap.Tq + XATT_ROWS - 1) / XATT_ROWS, heads, items), XATT_THREADS, 0, st>>>(ap);
+    SAB_CUDA(cudaGetLastError());
+    return;
+  }
   dim3 grid((ap.Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
-  mark(e, st, ap.k == ap.q ? "sdpa.self" : "sdpa.cross", 4.0 * items * heads * (double)ap.Tq * ap.Tk * 128, 0);
+  mark(e, st, ap.k == ap.q ? "sdpa.self" : "sdpa.cross", fl, 0);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(ap);
+  SAB_CUDA(cudaGetLastError());
+}
+
+static void launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& ap,
+                                int items, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SAB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+    configured = true;
+  }
+  dim3 grid((ap.Tq + 127) / 128, ap.heads, items);
+  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, st>>>(tq, tk, tv, ap);
   SAB_CUDA(cudaGetLastError());
 }
 
@@ -699,7 +726,15 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
     a.k = p.qkv; a.k_ld = 3 * d; a.k_col0 = d;
     a.v = p.qkv; a.v_ld = 3 * d; a.v_col0 = 2 * d;
     a.o = p.att; a.o_ld = d; a.key_mask = p.pad_mask; a.Tq = T; a.Tk = T; a.scale_log2 = sl2;
-    attention(e, a, Bc, H, st);
+    if (p.att_tc) {
+      AttnTcParams tp{};
+      tp.o = p.att; tp.o_ld = d; tp.key_mask = p.pad_mask; tp.Tq = T; tp.Tk = T; tp.heads = H;
+      tp.q_col0 = 0; tp.k_col0 = d; tp.v_col0 = 2 * d; tp.scale_log2 = sl2; tp.v_lbo = ATC_KV_BYTES / 2; tp.v_sbo = 1024;
+      mark(e, st, "sdpa.self", 4.0 * Bc * H * (double)T * T * 128, 0);
+      launch_attention_tc(p.tm_att_q, p.tm_att_kv, p.tm_att_kv, tp, Bc, st);
+    } else {
+      attention(e, a, Bc, H, st);
+    }
     gemm(e, o.wo, st);
     gemm(e, o.q_c, st);
     gemm(e, o.kv_c, st);
@@ -1314,9 +1349,31 @@ int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, cons
   a.q = (const bf16*)q; a.q_ld = ld; a.k = (const bf16*)k; a.k_ld = ld; a.v = (const bf16*)v; a.v_ld = ld;
   a.o = (bf16*)o; a.o_ld = ld; a.key_mask = key_mask; a.Tq = Tq; a.Tk = Tk;
   a.scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
-  dim3 grid((Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(a);
+  if (Tk <= XATT_MAX_TK && k != q) {
+    xattn_small_kernel<<<dim3((Tq + XATT_ROWS - 1) / XATT_ROWS, heads, items), XATT_THREADS, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    dim3 grid((Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
+    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(a);
+  }
   SAB_CUDA(cudaGetLastError());
+  SAB_API_END
+}
+
+int sab_test_attention_tc(int items, int heads, int T, const void* q, const void* k, const void* v,
+                          const uint8_t* key_mask, void* o, int v_lbo, int v_sbo, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(T <= 256, "tcgen05 attention handles T <= 256");
+  const long long ld = (long long)heads * 128;
+  CUtensorMap tq = make_tmap_3d(q, ld, T, items, ld, (int64_t)T * ld, 64, 128);
+  CUtensorMap tk = make_tmap_3d(k, ld, T, items, ld, (int64_t)T * ld, 64, 256);
+  CUtensorMap tv = make_tmap_3d(v, ld, T, items, ld, (int64_t)T * ld, 64, 256);
+  AttnTcParams tp{};
+  tp.o = (bf16*)o; tp.o_ld = ld; tp.key_mask = key_mask; tp.Tq = T; tp.Tk = T; tp.heads = heads;
+  tp.q_col0 = tp.k_col0 = tp.v_col0 = 0;
+  tp.scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+  tp.v_lbo = v_lbo > 0 ? v_lbo : ATC_KV_BYTES / 2;
+  tp.v_sbo = v_sbo > 0 ? v_sbo : 1024;
+  launch_attention_tc(tq, tk, tv, tp, items, (cudaStream_t)stream);
   SAB_API_END
 }
 

@@ -106,6 +106,55 @@ def stage_attn():
     return ok
 
 
+def stage_attn_tc():
+    """tcgen05 self-attention vs fp32 torch; also probes the MN-major V descriptor strides."""
+    L = _capi.lib()
+    ok_default = True
+    for (lbo, sbo) in [(0, 0), (1024, 32768), (32768, 128), (128, 1024)]:
+        for (items, heads, T, masked) in [(1, 1, 256, False), (2, 3, 250, True), (3, 2, 37, True), (2, 2, 129, False)]:
+            g = torch.Generator(device="cuda").manual_seed(T + items)
+            q, k, v = (torch.randn(items * T, heads * 128, device="cuda", generator=g).bfloat16() for _ in range(3))
+            mask = torch.ones(items, T, dtype=torch.uint8, device="cuda")
+            if masked:
+                for i in range(items):
+                    mask[i, max(1, T - 3 * (i + 1)):] = 0
+            o = torch.zeros(items * T, heads * 128, device="cuda", dtype=torch.bfloat16)
+            _capi.check(L.sab_test_attention_tc(items, heads, T, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                mask.data_ptr(), o.data_ptr(), lbo, sbo, _capi.stream_ptr()))
+            torch.cuda.synchronize()
+            qf, kf, vf = (x.float().view(items, T, heads, 128).permute(0, 2, 1, 3) for x in (q, k, v))
+            s = (qf @ kf.transpose(-1, -2) / 128 ** 0.5).masked_fill(~mask.bool()[:, None, None, :], float("-inf"))
+            ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(items * T, heads * 128)
+            e = rel(o.float(), ref)
+            good = e < 1e-2
+            if (lbo, sbo) == (0, 0):
+                ok_default &= good
+            print(f"attn_tc lbo={lbo} sbo={sbo} items={items} H={heads} T={T}: rel={e:.3e} {'OK' if good else 'FAIL'}", flush=True)
+            if not good and (lbo, sbo) == (0, 0):
+                d = (o.float() - ref)
+                print("   o[0,:8]", o[0, :8].float().tolist(), "\n   ref    ", ref[0, :8].tolist(), flush=True)
+                print("   o[0,64:72]", o[0, 64:72].float().tolist(), "\n   ref      ", ref[0, 64:72].tolist(), flush=True)
+    # timing at the bench shape
+    items, heads, T = 64, 22, 250
+    q, k, v = (torch.randn(items * T, heads * 128, device="cuda").bfloat16() for _ in range(3))
+    o = torch.zeros_like(q)
+    mask = torch.ones(items, T, dtype=torch.uint8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fn in (("tcgen05", lambda: L.sab_test_attention_tc(items, heads, T, q.data_ptr(), k.data_ptr(), v.data_ptr(), mask.data_ptr(), o.data_ptr(), 0, 0, _capi.stream_ptr())),
+                     ("mma.sync", lambda: L.sab_test_attention(items, heads, T, T, q.data_ptr(), k.data_ptr(), v.data_ptr(), mask.data_ptr(), o.data_ptr(), _capi.stream_ptr()))):
+        for _ in range(3):
+            _capi.check(fn())
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            _capi.check(fn())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"self-attention {name}: {ms * 1e3:.1f} us  {4 * items * heads * T * T * 128 / ms / 1e9:.1f} TFLOP/s", flush=True)
+    return ok_default
+
+
 def _tiny_model():
     from sam_audio_b200.model import build_synthetic_model
     return build_synthetic_model("sam-audio-tiny", seed=0)
@@ -220,7 +269,7 @@ if __name__ == "__main__":
     ap.add_argument("--model", default="sam-audio-base")
     ap.add_argument("--batch", type=int, default=8)
     a = ap.parse_args()
-    fn = {"gemm": stage_gemm, "attn": stage_attn, "dit": stage_dit, "codec": stage_codec,
+    fn = {"gemm": stage_gemm, "attn": stage_attn, "attn_tc": stage_attn_tc, "dit": stage_dit, "codec": stage_codec,
           "separate": stage_separate, "perf": lambda: stage_perf(a.model, a.batch)}[a.stage]
     ok = fn()
     print(f"STAGE {a.stage}: {'PASS' if ok else 'FAIL'}", flush=True)
