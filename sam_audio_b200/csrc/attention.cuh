@@ -208,10 +208,18 @@ attention_kernel(const AttnParams P) {
 
 // ---------------------------------------------------------------------------------------------
 // Cross-attention to a handful of text tokens (Tk <= 16: "man speaking" is 3 tokens).  HBM-bound:
-// one warp per (query row, head); K/V of the (item, head) live in shared memory; each lane owns 4 of the
-// 128 head dims; scores by warp-shuffle reduction, softmax in registers.  Reads Q once, writes O once.
+// 8 lanes per (query row, head), 16 head dims per lane (32 B loads, 256 B contiguous per row); K/V of the
+// (item, head) live in shared memory; scores by a 3-step shuffle reduction, softmax in registers.
+// Reads Q once, writes O once.
 // ---------------------------------------------------------------------------------------------
-constexpr int XATT_MAX_TK = 16, XATT_ROWS = 64, XATT_THREADS = 256;
+constexpr int XATT_MAX_TK = 16, XATT_ROWS = 128, XATT_THREADS = 256;
+SAB_DEVICE void bf16x8_to_f32(const uint4& r, float (&f)[8]) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.z));
+  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
 __global__ void __launch_bounds__(XATT_THREADS)
 xattn_small_kernel(const AttnParams P) {
   __shared__ __align__(16) __nv_bfloat16 sK[XATT_MAX_TK][ATT_D];
@@ -226,54 +234,81 @@ xattn_small_kernel(const AttnParams P) {
     *reinterpret_cast<uint4*>(&sK[j][c]) = *reinterpret_cast<const uint4*>(kb + (long long)j * P.k_ld + c);
     *reinterpret_cast<uint4*>(&sV[j][c]) = *reinterpret_cast<const uint4*>(vb + (long long)j * P.v_ld + c);
   }
-  if (tid < P.Tk) sBias[tid] = (!P.key_mask || P.key_mask[(long long)item * P.Tk + tid]) ? 0.f : -INFINITY;
-  __syncthreads();
-  const __nv_bfloat16* qb = P.q + (long long)item * P.Tq * P.q_ld + P.q_col0 + head * ATT_D + lane * 4;
-  __nv_bfloat16* ob = P.o + (long long)item * P.Tq * P.o_ld + head * ATT_D + lane * 4;
-  const int r_end = min(P.Tq, (qt + 1) * XATT_ROWS);
-  constexpr int kRowsPerWarp = XATT_ROWS / (XATT_THREADS / 32);   // 8: all query loads are issued up front
-  uint2 qraw[kRowsPerWarp];
+  if (tid < XATT_MAX_TK)
+    sBias[tid] = (tid < P.Tk && (!P.key_mask || P.key_mask[(long long)item * P.Tk + tid])) ? 0.f : -INFINITY;
+  // this lane: row (pass*32 + warp*4 + lane/8), dims [16*(lane%8), +16)
+  const int sub = lane >> 3, d0 = (lane & 7) * 16;
+  const __nv_bfloat16* qb = P.q + (long long)item * P.Tq * P.q_ld + P.q_col0 + head * ATT_D + d0;
+  __nv_bfloat16* ob = P.o + (long long)item * P.Tq * P.o_ld + head * ATT_D + d0;
+  constexpr int kPasses = XATT_ROWS / 32;
+  uint4 qraw[kPasses][2];
 #pragma unroll
-  for (int i = 0; i < kRowsPerWarp; ++i) {
-    const int r = qt * XATT_ROWS + warp + i * (XATT_THREADS / 32);
-    qraw[i] = make_uint2(0u, 0u);
-    if (r < r_end) qraw[i] = *reinterpret_cast<const uint2*>(qb + (long long)r * P.q_ld);
+  for (int p = 0; p < kPasses; ++p) {       // all query loads in flight before the K/V barrier
+    const int r = qt * XATT_ROWS + p * 32 + warp * 4 + sub;
+    qraw[p][0] = qraw[p][1] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < P.Tq) {
+      const uint4* src = reinterpret_cast<const uint4*>(qb + (long long)r * P.q_ld);
+      qraw[p][0] = src[0];
+      qraw[p][1] = src[1];
+    }
   }
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kRowsPerWarp; ++i) {
-    const int r = qt * XATT_ROWS + warp + i * (XATT_THREADS / 32);
-    const float2 q01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[i].x));
-    const float2 q23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[i].y));
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = qt * XATT_ROWS + p * 32 + warp * 4 + sub;
+    float qf[16];
+    { float t8[8]; bf16x8_to_f32(qraw[p][0], t8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qf[i] = t8[i];
+      bf16x8_to_f32(qraw[p][1], t8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qf[8 + i] = t8[i]; }
     float sc[XATT_MAX_TK];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < XATT_MAX_TK; ++j) {
       sc[j] = -INFINITY;
       if (j < P.Tk) {
-        const uint2 kraw = *reinterpret_cast<const uint2*>(&sK[j][lane * 4]);
-        const float2 k01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kraw.x));
-        const float2 k23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kraw.y));
-        float d = q01.x * k01.x + q01.y * k01.y + q23.x * k23.x + q23.y * k23.y;
-        d = warp_sum(d);
+        float kf[8], d = 0.f;
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sK[j][d0]), kf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sK[j][d0 + 8]), kf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d = fmaf(qf[8 + i], kf[i], d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
         sc[j] = d * P.scale_log2 + sBias[j];
         mx = fmaxf(mx, sc[j]);
       }
     }
-    float den = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    float den = 0.f, o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = 0.f;
 #pragma unroll
     for (int j = 0; j < XATT_MAX_TK; ++j) {
       if (j < P.Tk) {
-        const float pj = exp2f(sc[j] - mx);
+        float pj;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pj) : "f"(sc[j] - mx));
         den += pj;
-        const uint2 vraw = *reinterpret_cast<const uint2*>(&sV[j][lane * 4]);
-        const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vraw.x));
-        const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vraw.y));
-        o0 = fmaf(pj, v01.x, o0); o1 = fmaf(pj, v01.y, o1); o2 = fmaf(pj, v23.x, o2); o3 = fmaf(pj, v23.y, o3);
+        float vf[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sV[j][d0]), vf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(pj, vf[i], o[i]);
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sV[j][d0 + 8]), vf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[8 + i] = fmaf(pj, vf[i], o[8 + i]);
       }
     }
     const float inv = 1.f / den;
-    if (r < r_end)
-      *reinterpret_cast<uint2*>(ob + (long long)r * P.o_ld) = make_uint2(pack_bf16(o0 * inv, o1 * inv), pack_bf16(o2 * inv, o3 * inv));
+    if (r < P.Tq) {
+      uint4* dst = reinterpret_cast<uint4*>(ob + (long long)r * P.o_ld);
+      dst[0] = make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv),
+                          pack_bf16(o[4] * inv, o[5] * inv), pack_bf16(o[6] * inv, o[7] * inv));
+      dst[1] = make_uint4(pack_bf16(o[8] * inv, o[9] * inv), pack_bf16(o[10] * inv, o[11] * inv),
+                          pack_bf16(o[12] * inv, o[13] * inv), pack_bf16(o[14] * inv, o[15] * inv));
+    }
   }
 }
 

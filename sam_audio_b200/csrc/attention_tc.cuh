@@ -1,7 +1,10 @@
 // tcgen05 self-attention for sequences of up to 256 keys (10 s clips: T = 250), head_dim = 128.
 // reference: sam_audio/model/transformer.py:153-160 (SDPA, scale 1/sqrt(hd), bool key mask, True = attend).
 //
-// One CTA = 128 query rows of one (item, head).  Everything between the two HBM touches stays on chip:
+// One CTA = one (item, head): both 128-query tiles share one K/V load and run as two independent softmax
+// groups (warps 1-4 and 5-8, two warps per SM sub-partition) against one TMA/MMA issuing thread, so the second
+// tile's QK^T runs under the first tile's softmax and the first tile's PV under the second tile's softmax.
+// Everything between the two HBM touches stays on chip:
 //   TMA  : Q [128 x 128], K [256 x 128], V [256 x 128] tiles (SWIZZLE_128B, zero-filled past the sequence end)
 //   UMMA : S = Q K^T            (M=128, N=256, K=128: 8 x tcgen05.mma, A/B from shared memory) -> TMEM [0,256)
 //   CUDA : row softmax, thread == query row == TMEM lane: max / exp2 / sum straight out of TMEM,
@@ -16,10 +19,10 @@
 
 namespace sab {
 
-constexpr int ATC_THREADS = 160;                  // warp 0: TMA + MMA issue + TMEM alloc; warps 1..4: softmax
-constexpr int ATC_Q_BYTES = 128 * 128 * 2;        // 32 KB  (2 sub-tiles of [128 x 64])
+constexpr int ATC_THREADS = 288;                  // warp 0: TMA + MMA issue + TMEM alloc; warps 1..8: two softmax groups
+constexpr int ATC_Q_BYTES = 128 * 128 * 2;        // 32 KB per 128-query tile (2 sub-tiles of [128 x 64])
 constexpr int ATC_KV_BYTES = 256 * 128 * 2;       // 64 KB  (2 sub-tiles of [256 x 64])
-constexpr int ATC_SMEM = ATC_Q_BYTES + 2 * ATC_KV_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
+constexpr int ATC_SMEM = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
 
 struct AttnTcParams {
   __nv_bfloat16* o; long long o_ld;
@@ -74,31 +77,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
                     const __grid_constant__ CUtensorMap tm_v /*box 64 x 256*/, const __grid_constant__ AttnTcParams P) {
   extern __shared__ uint8_t atc_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATC_Q_BYTES;
+  uint8_t* sQ = smem;                              // two query tiles
+  uint8_t* sK = sQ + 2 * ATC_Q_BYTES;
   uint8_t* sV = sK + ATC_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATC_KV_BYTES);
-  uint64_t *bar_qk = bars, *bar_v = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t *bar_q0k = bars, *bar_q1 = bars + 1, *bar_v = bars + 2;
+  uint64_t *bar_s = bars + 3 /*[2]*/, *bar_p = bars + 5 /*[2]*/, *bar_o = bars + 7 /*[2]*/;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   uint32_t* kmask = tmem_slot + 4;   // 8 words: bit j of word c = key c*32 + j may be attended
 
-  const int mt = blockIdx.x, head = blockIdx.y, item = blockIdx.z;
+  const int head = blockIdx.x, item = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_mt = (P.Tq + 127) / 128;             // 1 or 2 query tiles
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_k);
       tma_prefetch_desc(&tm_v);
-      mbar_init(bar_qk, 1);
+      mbar_init(bar_q0k, 1);
+      mbar_init(bar_q1, 1);
       mbar_init(bar_v, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128);
-      mbar_init(bar_o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s + i, 1);
+        mbar_init(bar_p + i, 128);
+        mbar_init(bar_o + i, 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   } else if (warp == 1) {
     // key validity bitmask (sequence end + padding mask)
     const uint8_t* mk = P.key_mask ? P.key_mask + (long long)item * P.Tk : nullptr;
@@ -113,96 +121,117 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tP = tmem, tO = tmem + 128;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- loads ----
+      // ---- loads: (Q0, K) first so the first QK^T can start, then Q1, then V ----
       const int qc = P.q_col0 + head * 128, kc = P.k_col0 + head * 128, vc = P.v_col0 + head * 128;
-      mbar_expect_tx(bar_qk, ATC_Q_BYTES + ATC_KV_BYTES);
-      tma_load_3d(sQ, &tm_q, bar_qk, qc, mt * 128, item);
-      tma_load_3d(sQ + ATC_Q_BYTES / 2, &tm_q, bar_qk, qc + 64, mt * 128, item);
-      tma_load_3d(sK, &tm_k, bar_qk, kc, 0, item);
-      tma_load_3d(sK + ATC_KV_BYTES / 2, &tm_k, bar_qk, kc + 64, 0, item);
+      mbar_expect_tx(bar_q0k, ATC_Q_BYTES + ATC_KV_BYTES);
+      tma_load_3d(sQ, &tm_q, bar_q0k, qc, 0, item);
+      tma_load_3d(sQ + ATC_Q_BYTES / 2, &tm_q, bar_q0k, qc + 64, 0, item);
+      tma_load_3d(sK, &tm_k, bar_q0k, kc, 0, item);
+      tma_load_3d(sK + ATC_KV_BYTES / 2, &tm_k, bar_q0k, kc + 64, 0, item);
+      if (n_mt > 1) {
+        mbar_expect_tx(bar_q1, ATC_Q_BYTES);
+        tma_load_3d(sQ + ATC_Q_BYTES, &tm_q, bar_q1, qc, 128, item);
+        tma_load_3d(sQ + ATC_Q_BYTES + ATC_Q_BYTES / 2, &tm_q, bar_q1, qc + 64, 128, item);
+      }
       mbar_expect_tx(bar_v, ATC_KV_BYTES);
       tma_load_3d(sV, &tm_v, bar_v, vc, 0, item);
       tma_load_3d(sV + ATC_KV_BYTES / 2, &tm_v, bar_v, vc + 64, 0, item);
-      // ---- S = Q K^T ----
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      {
-        constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+      // ---- S_m = Q_m K^T  -> TMEM cols [256m, 256m + 256) ----
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256);
+      for (int m = 0; m < n_mt; ++m) {
+        mbar_wait(m == 0 ? bar_q0k : bar_q1, 0);
+        tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t qa = smem_u32(sQ) + (ks >> 2) * (ATC_Q_BYTES / 2);
+          const uint32_t qa = smem_u32(sQ) + m * ATC_Q_BYTES + (ks >> 2) * (ATC_Q_BYTES / 2);
           const uint32_t ka = smem_u32(sK) + (ks >> 2) * (ATC_KV_BYTES / 2);
-          umma_f16(tS, make_kmajor_desc<128>(qa) + (uint64_t)((ks & 3) * 2), make_kmajor_desc<128>(ka) + (uint64_t)((ks & 3) * 2),
-                   idesc, ks ? 1u : 0u);
+          umma_f16(tmem + m * 256, make_kmajor_desc<128>(qa) + (uint64_t)((ks & 3) * 2),
+                   make_kmajor_desc<128>(ka) + (uint64_t)((ks & 3) * 2), idesc_s, ks ? 1u : 0u);
         }
-        umma_commit(bar_s);
+        umma_commit(bar_s + m);
       }
-      // ---- O = P V ----
-      mbar_wait(bar_p, 0);
+      // ---- O_m = P_m V  (A = P from TMEM cols [256m, +128), D = cols [256m + 128, +128)) ----
+      constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 128);
       mbar_wait(bar_v, 0);
-      tc_fence_after();
-      {
-        constexpr uint32_t idesc = make_idesc_bf16_bmn(128, 128);
+      for (int m = 0; m < n_mt; ++m) {
+        mbar_wait(bar_p + m, 0);
+        tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 16; ++ks) {      // 16 keys per instruction
           const uint64_t vb = make_mnmajor_desc(smem_u32(sV) + ks * 16 * 128, (uint32_t)P.v_lbo, (uint32_t)P.v_sbo);
-          umma_f16_ts(tO, tP + ks * 8, vb, idesc, ks ? 1u : 0u);
+          umma_f16_ts(tmem + m * 256 + 128, tmem + m * 256 + ks * 8, vb, idesc_o, ks ? 1u : 0u);
         }
-        umma_commit(bar_o);
+        umma_commit(bar_o + m);
       }
     }
-  } else {
-    // ===================== softmax / epilogue: thread == query row =====================
+  } else if (((warp - 1) >> 2) < n_mt) {
+    // ===================== softmax / epilogue group m: thread == query row == TMEM lane =====================
+    const int m = (warp - 1) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int t = mt * 128 + row;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    mbar_wait(bar_s, 0);
+    const int t = m * 128 + row;
+    const uint32_t tS = tmem + m * 256 + ((uint32_t)(q * 32) << 16);
+    const uint32_t tO = tS + 128;
+    mbar_wait(bar_s + m, 0);
     tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
       float v[32];
-      tmem_ld32(tS + lane_addr + c * 32, v);
+      tmem_ld32(tS + c * 32, v);
       tmem_ld_wait();
       const uint32_t bits = kmask[c];
+      if (bits == 0xffffffffu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((bits >> j) & 1u) ? v[j] : -INFINITY);
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((bits >> j) & 1u) ? v[j] : -INFINITY);
+      }
     }
     const float mscaled = (mx == -INFINITY) ? 0.f : mx * P.scale_log2;
     float sum = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
       float v[32];
-      tmem_ld32(tS + lane_addr + c * 32, v);
+      tmem_ld32(tS + c * 32, v);
       tmem_ld_wait();
       const uint32_t bits = kmask[c];
       uint32_t pk[16];
+      if (bits == 0xffffffffu) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float p0 = ((bits >> j) & 1u) ? ex2_approx(fmaf(v[j], P.scale_log2, -mscaled)) : 0.f;
-        const float p1 = ((bits >> (j + 1)) & 1u) ? ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled)) : 0.f;
-        sum += p0 + p1;
-        pk[j >> 1] = pack_bf16(p0, p1);
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = ex2_approx(fmaf(v[j], P.scale_log2, -mscaled));
+          const float p1 = ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled));
+          sum += p0 + p1;
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = ((bits >> j) & 1u) ? ex2_approx(fmaf(v[j], P.scale_log2, -mscaled)) : 0.f;
+          const float p1 = ((bits >> (j + 1)) & 1u) ? ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled)) : 0.f;
+          sum += p0 + p1;
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
       }
-      tmem_st16(tP + lane_addr + c * 16, pk);   // in place: cols [16c, 16c+16) were consumed by chunk c/2 <= c
+      tmem_st16(tS + c * 16, pk);   // in place: cols [16c, 16c+16) were consumed by chunk c/2 <= c
     }
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(bar_p);
+    mbar_arrive(bar_p + m);
     // ---- O / sum -> global ----
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_o + m, 0);
     tc_fence_after();
     const float inv = 1.f / sum;
     __nv_bfloat16* op = P.o + ((long long)item * P.Tq + t) * P.o_ld + head * 128;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       float v[32];
-      tmem_ld32(tO + lane_addr + c * 32, v);
+      tmem_ld32(tO + c * 32, v);
       tmem_ld_wait();
       if (t < P.Tq) {
         uint4* dst = reinterpret_cast<uint4*>(op + c * 32);
@@ -217,7 +246,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem);
+    tmem_dealloc<512>(tmem);
   }
 }
 

@@ -667,7 +667,7 @@ static void launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, co
     SAB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
     configured = true;
   }
-  dim3 grid((ap.Tq + 127) / 128, ap.heads, items);
+  dim3 grid(ap.heads, items);
   attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, st>>>(tq, tk, tv, ap);
   SAB_CUDA(cudaGetLastError());
 }
