@@ -213,28 +213,43 @@ attention_kernel(const AttnParams P) {
 // Reads Q once, writes O once.
 // ---------------------------------------------------------------------------------------------
 constexpr int XATT_MAX_TK = 16, XATT_ROWS = 128, XATT_THREADS = 256;
-SAB_DEVICE void bf16x8_to_f32(const uint4& r, float (&f)[8]) {
+SAB_DEVICE void bf16x8_to_f32(const uint4& r, float* f) {
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
   const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
   const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.z));
   const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.w));
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+// TK = compile-time key count bucket (keys >= P.Tk are zero rows with a -inf bias), so every loop is straight-line
+template <int TK>
 __global__ void __launch_bounds__(XATT_THREADS)
 xattn_small_kernel(const AttnParams P) {
-  __shared__ __align__(16) __nv_bfloat16 sK[XATT_MAX_TK][ATT_D];
-  __shared__ __align__(16) __nv_bfloat16 sV[XATT_MAX_TK][ATT_D];
-  __shared__ float sBias[XATT_MAX_TK];
+  __shared__ __align__(16) float sK[TK][ATT_D];
+  __shared__ __align__(16) float sV[TK][ATT_D];
+  __shared__ float sBias[TK];
   const int qt = blockIdx.x, head = blockIdx.y, item = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __nv_bfloat16* kb = P.k + (long long)item * P.Tk * P.k_ld + P.k_col0 + head * ATT_D;
   const __nv_bfloat16* vb = P.v + (long long)item * P.Tk * P.v_ld + P.v_col0 + head * ATT_D;
-  for (int i = tid; i < P.Tk * (ATT_D / 8); i += XATT_THREADS) {   // 16 B per thread
+  for (int i = tid; i < TK * (ATT_D / 8); i += XATT_THREADS) {   // 8 dims per thread, converted to fp32 once
     const int j = i / (ATT_D / 8), c = (i % (ATT_D / 8)) * 8;
-    *reinterpret_cast<uint4*>(&sK[j][c]) = *reinterpret_cast<const uint4*>(kb + (long long)j * P.k_ld + c);
-    *reinterpret_cast<uint4*>(&sV[j][c]) = *reinterpret_cast<const uint4*>(vb + (long long)j * P.v_ld + c);
+    uint4 kr = make_uint4(0u, 0u, 0u, 0u), vr = kr;
+    if (j < P.Tk) {
+      kr = *reinterpret_cast<const uint4*>(kb + (long long)j * P.k_ld + c);
+      vr = *reinterpret_cast<const uint4*>(vb + (long long)j * P.v_ld + c);
+    }
+    // shared layout: lane group l8 = dim/16 owns dims [16 l8, +16) as four float4 "i"; float4 (i, l8) sits at
+    // index i*8 + l8 so that the 8 lanes of a row read consecutive 16 B words (no bank conflicts)
+    float kf[8], vf[8];
+    bf16x8_to_f32(kr, kf);
+    bf16x8_to_f32(vr, vf);
+    const int l8 = c >> 4, i0 = (c & 15) >> 2;
+    *reinterpret_cast<float4*>(&sK[j][((i0) * 8 + l8) * 4]) = make_float4(kf[0], kf[1], kf[2], kf[3]);
+    *reinterpret_cast<float4*>(&sK[j][((i0 + 1) * 8 + l8) * 4]) = make_float4(kf[4], kf[5], kf[6], kf[7]);
+    *reinterpret_cast<float4*>(&sV[j][((i0) * 8 + l8) * 4]) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+    *reinterpret_cast<float4*>(&sV[j][((i0 + 1) * 8 + l8) * 4]) = make_float4(vf[4], vf[5], vf[6], vf[7]);
   }
-  if (tid < XATT_MAX_TK)
+  if (tid < TK)
     sBias[tid] = (tid < P.Tk && (!P.key_mask || P.key_mask[(long long)item * P.Tk + tid])) ? 0.f : -INFINITY;
   // this lane: row (pass*32 + warp*4 + lane/8), dims [16*(lane%8), +16)
   const int sub = lane >> 3, d0 = (lane & 7) * 16;
@@ -253,52 +268,42 @@ xattn_small_kernel(const AttnParams P) {
     }
   }
   __syncthreads();
-#pragma unroll
+#pragma unroll 1
   for (int p = 0; p < kPasses; ++p) {
     const int r = qt * XATT_ROWS + p * 32 + warp * 4 + sub;
-    float qf[16];
-    { float t8[8]; bf16x8_to_f32(qraw[p][0], t8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) qf[i] = t8[i];
-      bf16x8_to_f32(qraw[p][1], t8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) qf[8 + i] = t8[i]; }
-    float sc[XATT_MAX_TK];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < XATT_MAX_TK; ++j) {
-      sc[j] = -INFINITY;
-      if (j < P.Tk) {
-        float kf[8], d = 0.f;
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sK[j][d0]), kf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sK[j][d0 + 8]), kf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d = fmaf(qf[8 + i], kf[i], d);
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        sc[j] = d * P.scale_log2 + sBias[j];
-        mx = fmaxf(mx, sc[j]);
-      }
-    }
-    float den = 0.f, o[16];
+    float qf[16], o[16];
+    bf16x8_to_f32(qraw[p][0], qf);
+    bf16x8_to_f32(qraw[p][1], qf + 8);
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, den = 0.f;     // online softmax over the (few) keys keeps the live state small
+#pragma unroll 4
+    for (int j = 0; j < TK; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(&sK[j][0]) + (lane & 7);
+      float d = 0.f;
 #pragma unroll
-    for (int j = 0; j < XATT_MAX_TK; ++j) {
-      if (j < P.Tk) {
-        float pj;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pj) : "f"(sc[j] - mx));
-        den += pj;
-        float vf[8];
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sV[j][d0]), vf);
+      for (int i = 0; i < 4; ++i) {
+        const float4 k4 = kr[i * 8];
+        d = fmaf(qf[4 * i], k4.x, d); d = fmaf(qf[4 * i + 1], k4.y, d);
+        d = fmaf(qf[4 * i + 2], k4.z, d); d = fmaf(qf[4 * i + 3], k4.w, d);
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      const float s = fmaf(d, P.scale_log2, sBias[j]);
+      const float m_new = fmaxf(m_run, s);
+      const float base = (m_new == -INFINITY) ? 0.f : m_new;
+      float corr, pj;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"(m_run - base));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pj) : "f"(s - base));
+      m_run = m_new;
+      den = fmaf(den, corr, pj);
+      const float4* vr = reinterpret_cast<const float4*>(&sV[j][0]) + (lane & 7);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(pj, vf[i], o[i]);
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(&sV[j][d0 + 8]), vf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[8 + i] = fmaf(pj, vf[i], o[8 + i]);
+      for (int i = 0; i < 4; ++i) {
+        const float4 v4 = vr[i * 8];
+        o[4 * i] = fmaf(o[4 * i], corr, pj * v4.x); o[4 * i + 1] = fmaf(o[4 * i + 1], corr, pj * v4.y);
+        o[4 * i + 2] = fmaf(o[4 * i + 2], corr, pj * v4.z); o[4 * i + 3] = fmaf(o[4 * i + 3], corr, pj * v4.w);
       }
     }
     const float inv = 1.f / den;
@@ -310,6 +315,12 @@ xattn_small_kernel(const AttnParams P) {
                           pack_bf16(o[12] * inv, o[13] * inv), pack_bf16(o[14] * inv, o[15] * inv));
     }
   }
+}
+inline void launch_xattn_small(const AttnParams& ap, int items, int heads, cudaStream_t st) {
+  const dim3 grid((ap.Tq + XATT_ROWS - 1) / XATT_ROWS, heads, items);
+  if (ap.Tk <= 4) xattn_small_kernel<4><<<grid, XATT_THREADS, 0, st>>>(ap);
+  else if (ap.Tk <= 8) xattn_small_kernel<8><<<grid, XATT_THREADS, 0, st>>>(ap);
+  else xattn_small_kernel<16><<<grid, XATT_THREADS, 0, st>>>(ap);
 }
 
 }  // namespace sab

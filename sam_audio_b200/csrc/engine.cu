@@ -650,7 +650,7 @@ static void attention(sab_engine* e, const AttnParams& ap, int items, int heads,
   const double fl = 4.0 * items * heads * (double)ap.Tq * ap.Tk * 128;
   if (ap.Tk <= XATT_MAX_TK && ap.k != ap.q) {   // a handful of text tokens: HBM-bound warp-per-row kernel
     mark(e, st, "sdpa.cross", fl, (double)items * ap.Tq * heads * 128 * 4.0);
-    xattn_small_kernel<<<dim3((ap.Tq + XATT_ROWS - 1) / XATT_ROWS, heads, items), XATT_THREADS, 0, st>>>(ap);
+    launch_xattn_small(ap, items, heads, st);
     SAB_CUDA(cudaGetLastError());
     return;
   }
@@ -1350,7 +1350,7 @@ int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, cons
   a.o = (bf16*)o; a.o_ld = ld; a.key_mask = key_mask; a.Tq = Tq; a.Tk = Tk;
   a.scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
   if (Tk <= XATT_MAX_TK && k != q) {
-    xattn_small_kernel<<<dim3((Tq + XATT_ROWS - 1) / XATT_ROWS, heads, items), XATT_THREADS, 0, (cudaStream_t)stream>>>(a);
+    launch_xattn_small(a, items, heads, (cudaStream_t)stream);
   } else {
     dim3 grid((Tq + ATT_BQ - 1) / ATT_BQ, heads, items);
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(a);
