@@ -358,6 +358,10 @@ def run_gpu(args):
             groups["dit_gemm"] += v["ms"]
         else:
             groups["norm_elementwise"] += v["ms"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r1.json")
+    if os.path.exists(tpath):     # dram__bytes_read+write of the dominant launch (ffn.w13) from the committed ncu capture
+        traffic = json.load(open(tpath))
     att = {t: v for t, v in prof.items() if t.startswith("sdpa")}
     att_tf = sum(v["flops"] for v in att.values()) / max(sum(v["ms"] for v in att.values()), 1e-9) / 1e9
     line = {
@@ -371,7 +375,11 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"kernel": "gemm_tc_kernel (tcgen05 segmented GEMM: DiT linears + codec convs)",
                      "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                     "frac": achieved / peaks["tf_sustained"],
+                     "traffic": None if traffic is None else traffic["traffic_bytes_per_launch"],
+                     "traffic_note": None if traffic is None else
+                     f"{traffic['kernel']}: dram read+write per launch from ncu --set full "
+                     f"(algorithmic {traffic['algorithmic_bytes_per_launch']} B); {traffic['source']}",
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                      "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
                      "share_of_step": g_ms / max(total_ms, 1e-9),
