@@ -286,7 +286,8 @@ def run_gpu(args):
 
     def step_e2e():
         batch = proc(descriptions=desc, audios=clips)               # host: mono mix, pad, masks, anchors
-        batch.audios = batch.audios.pin_memory()
+        if not batch.audios.is_pinned():
+            batch.audios = batch.audios.pin_memory()
         batch = batch.to(dev)                                       # H2D
         out = model.separate(batch, noise=noise_host.to(dev, non_blocking=True))
         loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])

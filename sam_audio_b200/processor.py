@@ -39,7 +39,8 @@ def batch_audio(audios: Sequence[AudioLike], audio_sampling_rate: int = 48_000):
         monos.append(w.mean(0))
     lengths = torch.tensor([m.size(-1) for m in monos])
     longest = int(lengths.max()) if len(monos) else 0
-    out = monos[0].new_zeros(len(monos), 1, longest)
+    pinned = len(monos) > 0 and all(m.device.type == "cpu" and m.is_pinned() for m in monos)
+    out = torch.zeros(len(monos), 1, longest, dtype=monos[0].dtype, device=monos[0].device, pin_memory=pinned)
     for i, m in enumerate(monos):
         out[i, 0, : m.size(-1)] = m
     return out, lengths
