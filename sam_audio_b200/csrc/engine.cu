@@ -225,6 +225,7 @@ struct sab_engine {
   int64_t staging_elems = 0;
   bool finalized = false;
   int64_t launches = 0;
+  cudaStream_t capture_stream = nullptr;   // private stream for graph capture (the caller's may be the NULL stream)
   bool prof = false;
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_events;
@@ -510,6 +511,14 @@ struct DitPlan {
   CUtensorMap tm_att_q, tm_att_kv;   // fused-QKV buffer viewed as (3d cols, T rows, Bc items): box 64x128 / 64x256
   bool att_tc = false;               // tcgen05 self-attention usable (T <= 256)
   double flops_per_eval = 0;
+  // the whole ODE solve (2*n_steps evaluations, ~9k launches) as one CUDA graph, captured on the second solve
+  // of a plan (the first one runs eagerly and configures every kernel's attributes)
+  cudaGraphExec_t solve_graph = nullptr;
+  int solve_graph_steps = 0;
+  int64_t solve_graph_launches = 0;
+  int solves = 0;
+  int time_steps_uploaded = 0;
+  ~DitPlan() { if (solve_graph) cudaGraphExecDestroy(solve_graph); }
 };
 
 static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
@@ -969,6 +978,7 @@ sab_engine::~sab_engine() {
   enc_plans.clear();
   dec_plans.clear();
   if (staging) cudaFree(staging);
+  if (capture_stream) cudaStreamDestroy(capture_stream);
   for (auto ev : prof_events) cudaEventDestroy(ev);
 }
 
@@ -1149,26 +1159,60 @@ int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, voi
   cudaStream_t st = (cudaStream_t)stream;
   DitPlan& p = *e->dit;
   const long long n = p.M * 256;
-  // evaluation times k/n and (k + 1/2)/n, broadcast over the batch (model.py:280 t.expand)
-  std::vector<float> times((size_t)2 * n_steps * p.Bc);
-  for (int k = 0; k < n_steps; ++k)
-    for (int b = 0; b < p.Bc; ++b) {
-      times[(size_t)(2 * k) * p.Bc + b] = (float)k / (float)n_steps;
-      times[(size_t)(2 * k + 1) * p.Bc + b] = ((float)k + 0.5f) / (float)n_steps;
-    }
-  SAB_CUDA(cudaMemcpyAsync(p.time_dev, times.data(), times.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-  SAB_CUDA(cudaStreamSynchronize(st));  // `times` is a stack-owned host buffer
-  SAB_CUDA(cudaMemcpyAsync(p.y, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  mark(e, st, "cast_bf16_kernel");
-  cast_bf16_kernel<<<512, 256, 0, st>>>(p.y, p.y_bf, n);
-  const float dt = 1.0f / (float)n_steps;
-  for (int k = 0; k < n_steps; ++k) {
-    // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)
-    FinalSpec a{p.y, 0.5f * dt, p.ymid, p.y_bf};
-    dit_eval(e, p.time_dev + (size_t)(2 * k) * p.Bc, a, st);
-    FinalSpec b{p.y, dt, p.y, p.y_bf};
-    dit_eval(e, p.time_dev + (size_t)(2 * k + 1) * p.Bc, b, st);
+  // evaluation times k/n and (k + 1/2)/n, broadcast over the batch (model.py:280 t.expand); uploaded once per plan
+  if (p.time_steps_uploaded != n_steps) {
+    std::vector<float> times((size_t)2 * n_steps * p.Bc);
+    for (int k = 0; k < n_steps; ++k)
+      for (int b = 0; b < p.Bc; ++b) {
+        times[(size_t)(2 * k) * p.Bc + b] = (float)k / (float)n_steps;
+        times[(size_t)(2 * k + 1) * p.Bc + b] = ((float)k + 0.5f) / (float)n_steps;
+      }
+    SAB_CUDA(cudaMemcpyAsync(p.time_dev, times.data(), times.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    SAB_CUDA(cudaStreamSynchronize(st));  // `times` is a stack-owned host buffer
+    p.time_steps_uploaded = n_steps;
   }
+  SAB_CUDA(cudaMemcpyAsync(p.y, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  auto enqueue = [&](cudaStream_t st) {
+    mark(e, st, "cast_bf16_kernel");
+    cast_bf16_kernel<<<512, 256, 0, st>>>(p.y, p.y_bf, n);
+    const float dt = 1.0f / (float)n_steps;
+    for (int k = 0; k < n_steps; ++k) {
+      // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)
+      FinalSpec a{p.y, 0.5f * dt, p.ymid, p.y_bf};
+      dit_eval(e, p.time_dev + (size_t)(2 * k) * p.Bc, a, st);
+      FinalSpec b{p.y, dt, p.y, p.y_bf};
+      dit_eval(e, p.time_dev + (size_t)(2 * k + 1) * p.Bc, b, st);
+    }
+  };
+  static const bool use_graph = !getenv("SAB_NO_GRAPH");
+  const bool graphable = use_graph && !e->prof && p.solves >= 1;
+  if (graphable && (!p.solve_graph || p.solve_graph_steps != n_steps)) {
+    if (p.solve_graph) { SAB_CUDA(cudaGraphExecDestroy(p.solve_graph)); p.solve_graph = nullptr; }
+    const int64_t launches_before = e->launches;
+    cudaGraph_t g = nullptr;
+    if (!e->capture_stream) SAB_CUDA(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+    SAB_CUDA(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue(e->capture_stream);
+    } catch (...) {
+      cudaStreamEndCapture(e->capture_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    SAB_CUDA(cudaStreamEndCapture(e->capture_stream, &g));
+    SAB_CUDA(cudaGraphInstantiate(&p.solve_graph, g, 0));
+    SAB_CUDA(cudaGraphDestroy(g));
+    p.solve_graph_steps = n_steps;
+    p.solve_graph_launches = e->launches - launches_before;
+    e->launches = launches_before;   // counted when the graph is launched
+  }
+  if (graphable) {
+    SAB_CUDA(cudaGraphLaunch(p.solve_graph, st));
+    e->launches += p.solve_graph_launches;
+  } else {
+    enqueue(st);
+  }
+  p.solves++;
   SAB_CUDA(cudaMemcpyAsync(latent, p.y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   SAB_API_END
 }

@@ -325,6 +325,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (res0 && 4 * p < rl && n0 + c < P.N) r4[p] = *reinterpret_cast<const float4*>(res0 + p * res_step + c);
           }
         };
+        long long goff[8];                      // adaLN gate row of each pass (one integer division per tile, not per chunk)
+        if (P.gate) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            goff[p] = (4 * p < rl) ? (long long)((int)(row0 + 4 * p) / P.gate_div) * P.gate_ld : 0;
+        }
         load_res(half * 32, rr);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -348,8 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float* g0 = P.gate + n;
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-              const long long row = row0 + 4 * p;
-              const float4 g = __ldg(reinterpret_cast<const float4*>(g0 + ((4 * p < rl) ? (row / P.gate_div) : 0) * P.gate_ld));
+              const float4 g = __ldg(reinterpret_cast<const float4*>(g0 + goff[p]));
               x[p].x *= g.x; x[p].y *= g.y; x[p].z *= g.z; x[p].w *= g.w;
             }
           }
@@ -417,6 +422,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
       } else {  // EPI_QKV: each 128-col group is one head; this warp owns heads half, half+2, ... (BN=256: one each)
+        int pos[8];                             // RoPE position of each pass (one modulo per tile)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) pos[p] = (int)((row0 + 4 * p) % P.rope_T);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         constexpr int kHeadStep = (BN >= 256) ? 256 : 128;   // BN=128: both warps of a quarter share the single head
@@ -459,8 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (P.use_rope) {
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
-                  const int pos = (int)((row0 + 4 * p) % P.rope_T);
-                  const float4 cs = __ldg(reinterpret_cast<const float4*>(P.rope + (long long)pos * 64 + (cc >> 1)));
+                  const float4 cs = __ldg(reinterpret_cast<const float4*>(P.rope + (long long)pos[p] * 64 + (cc >> 1)));
                   const float a0 = x[p].x * cs.x - x[p].y * cs.y, a1 = x[p].x * cs.y + x[p].y * cs.x;
                   const float b0 = x[p].z * cs.z - x[p].w * cs.w, b1 = x[p].z * cs.w + x[p].w * cs.z;
                   x[p] = make_float4(a0, a1, b0, b1);

@@ -33,13 +33,13 @@ def _load_audio_file(path: str, sr: int) -> torch.Tensor:
 
 def batch_audio(audios: Sequence[AudioLike], audio_sampling_rate: int = 48_000):
     """Channel-mean mono mix, right zero-pad to the longest clip -> ([B,1,S], lengths int64)."""
-    monos = []
+    monos, pinned = [], len(audios) > 0
     for a in audios:
         w = _load_audio_file(a, audio_sampling_rate) if isinstance(a, str) else a
+        pinned = pinned and w.device.type == "cpu" and w.is_pinned()   # pinned in -> pinned batch out (async H2D)
         monos.append(w.mean(0))
     lengths = torch.tensor([m.size(-1) for m in monos])
     longest = int(lengths.max()) if len(monos) else 0
-    pinned = len(monos) > 0 and all(m.device.type == "cpu" and m.is_pinned() for m in monos)
     out = torch.zeros(len(monos), 1, longest, dtype=monos[0].dtype, device=monos[0].device, pin_memory=pinned)
     for i, m in enumerate(monos):
         out[i, 0, : m.size(-1)] = m
