@@ -510,6 +510,7 @@ struct DitPlan {
   std::vector<LayerOps> lay;
   CUtensorMap tm_att_q, tm_att_kv;   // fused-QKV buffer viewed as (3d cols, T rows, Bc items): box 64x128 / 64x256
   bool att_tc = false;               // tcgen05 self-attention usable (T <= 256)
+  bool xa_fused = false;             // cross-attention folded into the cross.wq GEMM epilogue (L <= XA_MAX_TK)
   double flops_per_eval = 0;
   // the whole ODE solve (2*n_steps evaluations, ~9k launches) as one CUDA graph, captured on the second solve
   // of a plan (the first one runs eagerly and configures every kernel's attributes)
@@ -583,6 +584,7 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
   }
   // ---- layers ----
   p.lay.resize(NL);
+  p.xa_fused = (L <= XA_MAX_TK) && !getenv("SAB_NO_FUSED_XATTN");
   for (int l = 0; l < NL; ++l) {
     const LayerW& W = e->layers[l];
     LayerOps& o = p.lay[l];
@@ -599,6 +601,15 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
     o.q_c.P.out_bf16 = p.qc; o.q_c.P.out_bf16_ld = d;
     o.q_c.P.qnorm_w = W.qn_c; o.q_c.P.knorm_w = W.kn_c; o.q_c.P.n_q_end = d; o.q_c.P.n_k_end = d;
     o.q_c.P.rope_T = T; o.q_c.P.use_rope = 0; o.q_c.P.eps = c.norm_eps;
+    if (p.xa_fused) {   // epilogue attends to the layer's text K/V and writes the attention output directly
+      SAB_CHECK(o.q_c.BN == 256, "fused cross-attention needs BN=256 tiles");
+      o.q_c.tag = "cross.wq+attn";
+      o.q_c.P.out_bf16 = p.att; o.q_c.P.out_bf16_ld = d;
+      o.q_c.P.xa_kv = p.kvc; o.q_c.P.xa_kv_ld = 2 * d; o.q_c.P.xa_v_col0 = d; o.q_c.P.xa_Tk = L; o.q_c.P.xa_T = T;
+      o.q_c.P.xa_mask = p.text_mask;
+      o.q_c.P.xa_scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+      o.q_c.flops += 4.0 * Bc * c.n_heads * (double)T * L * 128;
+    }
     o.kv_c = make_linear("cross.wkv", p.ymem, ML, d, W.wkv_c, 2 * d, 256, EPI_QKV);
     o.kv_c.P.out_bf16 = p.kvc; o.kv_c.P.out_bf16_ld = 2 * d;
     o.kv_c.P.qnorm_w = W.qn_c; o.kv_c.P.knorm_w = W.kn_c; o.kv_c.P.n_q_end = 0; o.kv_c.P.n_k_end = d;
@@ -745,14 +756,16 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
       attention(e, a, Bc, H, st);
     }
     gemm(e, o.wo, st);
-    gemm(e, o.q_c, st);
     gemm(e, o.kv_c, st);
-    AttnParams x{};
-    x.q = p.qc; x.q_ld = d; x.q_col0 = 0;
-    x.k = p.kvc; x.k_ld = 2 * d; x.k_col0 = 0;
-    x.v = p.kvc; x.v_ld = 2 * d; x.v_col0 = d;
-    x.o = p.att; x.o_ld = d; x.key_mask = p.text_mask; x.Tq = T; x.Tk = L; x.scale_log2 = sl2;
-    attention(e, x, Bc, H, st);
+    gemm(e, o.q_c, st);
+    if (!p.xa_fused) {
+      AttnParams x{};
+      x.q = p.qc; x.q_ld = d; x.q_col0 = 0;
+      x.k = p.kvc; x.k_ld = 2 * d; x.k_col0 = 0;
+      x.v = p.kvc; x.v_ld = 2 * d; x.v_col0 = d;
+      x.o = p.att; x.o_ld = d; x.key_mask = p.text_mask; x.Tq = T; x.Tk = L; x.scale_log2 = sl2;
+      attention(e, x, Bc, H, st);
+    }
     gemm(e, o.wo_c, st);
     rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st);
     gemm(e, o.w13, st);

@@ -65,7 +65,13 @@ struct GemmParams {
   const float* qnorm_w; const float* knorm_w;  // [128]
   int n_q_end, n_k_end;                        // cols [0,n_q_end): q-norm, [n_q_end,n_k_end): k-norm, rest plain
   const float2* rope; int rope_T; int use_rope; float eps;
+  // fused cross-attention to a few text tokens (QKV mode, all heads are queries): instead of writing the normalised
+  // queries, the epilogue attends to K/V [items*Tk, ld] (head-major columns; V at +xa_v_col0) and writes O
+  const __nv_bfloat16* xa_kv; long long xa_kv_ld; int xa_v_col0; int xa_Tk; int xa_T;
+  const uint8_t* xa_mask;   // [items, Tk] or null
+  float xa_scale_log2;
 };
+constexpr int XA_MAX_TK = 8;
 
 template <int BN, int BK, int CG>
 struct GemmSmem {
@@ -433,6 +439,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nh = n0 + hc;
           if (nh >= P.N) break;
           const float* nw = (nh < P.n_q_end) ? P.qnorm_w : (nh < P.n_k_end ? P.knorm_w : nullptr);
+          if (P.xa_kv != nullptr) {
+            // ---- fused cross-attention (thread == query row; scores are linear in the un-normalised query) ----
+            const int t_thr = t_base + lane;                                   // row inside the GEMM item
+            const long long grow = (long long)item * P.rows_per_item + (t_thr < P.rows_per_item ? t_thr : P.rows_per_item - 1);
+            const int b = (int)(grow / P.xa_T);
+            const __nv_bfloat16* kp = P.xa_kv + (long long)b * P.xa_Tk * P.xa_kv_ld + nh;
+            const __nv_bfloat16* vp = kp + P.xa_v_col0;
+            float ss = 0.f, sc[XA_MAX_TK];
+#pragma unroll
+            for (int j = 0; j < XA_MAX_TK; ++j) sc[j] = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+              float v[32];
+              tmem_ld32(t_addr + hc + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + c + i));
+                ss = fmaf(v[i], v[i], ss); ss = fmaf(v[i + 1], v[i + 1], ss);
+                ss = fmaf(v[i + 2], v[i + 2], ss); ss = fmaf(v[i + 3], v[i + 3], ss);
+                v[i] *= w4.x; v[i + 1] *= w4.y; v[i + 2] *= w4.z; v[i + 3] *= w4.w;
+              }
+#pragma unroll
+              for (int j = 0; j < XA_MAX_TK; ++j) {
+                if (j < P.xa_Tk) {
+                  const uint4* kr = reinterpret_cast<const uint4*>(kp + (long long)j * P.xa_kv_ld + c);
+                  float d = 0.f;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint4 k8 = __ldg(kr + i);
+                    const float2 k0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&k8.x));
+                    const float2 k1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&k8.y));
+                    const float2 k2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&k8.z));
+                    const float2 k3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&k8.w));
+                    d = fmaf(v[8 * i], k0.x, d); d = fmaf(v[8 * i + 1], k0.y, d);
+                    d = fmaf(v[8 * i + 2], k1.x, d); d = fmaf(v[8 * i + 3], k1.y, d);
+                    d = fmaf(v[8 * i + 4], k2.x, d); d = fmaf(v[8 * i + 5], k2.y, d);
+                    d = fmaf(v[8 * i + 6], k3.x, d); d = fmaf(v[8 * i + 7], k3.y, d);
+                  }
+                  sc[j] += d;
+                }
+              }
+            }
+            const float rstd = rsqrtf(ss * (1.f / 128.f) + P.eps);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < XA_MAX_TK; ++j) {
+              const bool ok = j < P.xa_Tk && (!P.xa_mask || P.xa_mask[(long long)b * P.xa_Tk + j]);
+              sc[j] = ok ? sc[j] * rstd * P.xa_scale_log2 : -INFINITY;
+              mx = fmaxf(mx, sc[j]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < XA_MAX_TK; ++j) {
+              float pj;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pj) : "f"(sc[j] - mx));
+              sc[j] = pj;
+              den += pj;
+            }
+            const float inv = 1.f / den;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+              float o[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0.f;
+#pragma unroll
+              for (int j = 0; j < XA_MAX_TK; ++j) {
+                if (j < P.xa_Tk) {
+                  const uint4* vr = reinterpret_cast<const uint4*>(vp + (long long)j * P.xa_kv_ld + c);
+                  const float pj = sc[j] * inv;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint4 v8 = __ldg(vr + i);
+                    const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v8.x));
+                    const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v8.y));
+                    const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v8.z));
+                    const float2 v3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v8.w));
+                    o[8 * i] = fmaf(pj, v0.x, o[8 * i]); o[8 * i + 1] = fmaf(pj, v0.y, o[8 * i + 1]);
+                    o[8 * i + 2] = fmaf(pj, v1.x, o[8 * i + 2]); o[8 * i + 3] = fmaf(pj, v1.y, o[8 * i + 3]);
+                    o[8 * i + 4] = fmaf(pj, v2.x, o[8 * i + 4]); o[8 * i + 5] = fmaf(pj, v2.y, o[8 * i + 5]);
+                    o[8 * i + 6] = fmaf(pj, v3.x, o[8 * i + 6]); o[8 * i + 7] = fmaf(pj, v3.y, o[8 * i + 7]);
+                  }
+                }
+              }
+              stage_put(o);
+              float4 x[8];
+              stage_get(x);
+              __nv_bfloat16* o0 = P.out_bf16 + row0 * P.out_bf16_ld + nh + c + tr_c;
+              const long long st = 4 * P.out_bf16_ld;
+#pragma unroll
+              for (int p = 0; p < 8; ++p)
+                if (4 * p < rl) *reinterpret_cast<uint2*>(o0 + p * st) = pack4_bf16(x[p]);
+              __syncwarp();
+            }
+            continue;
+          }
           float rstd = 1.f;   // of this thread's row (lane = row)
           if (nw) {
             float ss = 0.f;

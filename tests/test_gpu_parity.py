@@ -110,6 +110,28 @@ def test_dit_evaluation_vs_reference_golden(tiny_model, golden_dir):
         assert rel_l2(out.cpu(), g["out"][tag]) < 2e-2, tag
 
 
+@pytest.mark.parametrize("L", [1, 8, 12, 20])
+def test_dit_evaluation_text_lengths_vs_oracle(tiny_model, tiny_cfg, tiny_sd, L):
+    """Cross-attention paths by text length: fused into the cross.wq GEMM epilogue (L <= 8), the small-L kernel
+    (L <= 16) and the streaming kernel (L > 16) — each against the CPU oracle on the same inputs."""
+    from oracle import restate
+    g = torch.Generator().manual_seed(100 + L)
+    B, T = 2, 29
+    noisy = torch.randn(B, T, 256, generator=g)
+    f = torch.randn(B, T, 128, generator=g)
+    feats = torch.cat([f, f], 2)
+    text = torch.randn(B, L, 768, generator=g)
+    tmask = torch.ones(B, L, dtype=torch.bool)
+    tmask[1, max(1, L - 2):] = False
+    pad = restate.mask_from_sizes(torch.tensor([29.0, 17.0]))
+    ids, al = restate.process_anchors(None, pad, 1920, 48000)
+    time = torch.tensor([0.25, 0.75])
+    ref = restate.samaudio_forward(tiny_sd, tiny_cfg, noisy, feats, text, time, torch.zeros(B, 1024, T), tmask, ids, al, pad)
+    out = tiny_model.forward(noisy.cuda(), feats.cuda(), text.cuda(), time.cuda(), text_mask=tmask.cuda(),
+                             anchor_ids=ids.cuda(), anchor_alignment=al.cuda(), audio_pad_mask=pad.cuda())
+    assert rel_l2(out.cpu(), ref) < 2e-2
+
+
 def test_codec_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
     from oracle import restate
     from sam_audio_b200.synthetic import synthetic_clip
