@@ -132,6 +132,61 @@ def test_dit_evaluation_text_lengths_vs_oracle(tiny_model, tiny_cfg, tiny_sd, L)
     assert rel_l2(out.cpu(), ref) < 2e-2
 
 
+@pytest.fixture(scope="module")
+def small_model_and_sd():
+    """sam-audio-small stand-in (d=1536, 12 layers, 12 heads): production tile shapes, 2-CTA GEMMs, T=250."""
+    from sam_audio_b200.config import stand_in_config
+    from sam_audio_b200.model import SAMAudio
+    from sam_audio_b200.synthetic import make_state_dict
+    from sam_audio_b200.text_encoder import SyntheticTextEncoder
+    cfg = stand_in_config("sam-audio-small")
+    sd = make_state_dict(cfg, seed=1)
+    m = SAMAudio(cfg, text_encoder=SyntheticTextEncoder())
+    m.load_state_dict(sd)
+    return m.eval().cuda(), cfg, sd
+
+
+def test_dit_evaluation_production_shapes_vs_oracle(small_model_and_sd):
+    """One ODE function evaluation at production width and clip length (B=5 x T=250 -> M=1250 rows: cta_group::2 GEMM
+    pairs, tcgen05 self-attention, fused text cross-attention) vs the fp32 CPU oracle."""
+    from oracle import restate
+    m, cfg, sd = small_model_and_sd
+    g = torch.Generator().manual_seed(5)
+    B, T, L = 5, 250, 3
+    noisy = torch.randn(B, T, 256, generator=g)
+    f = torch.randn(B, T, 128, generator=g)
+    feats = torch.cat([f, f], 2)
+    text = torch.randn(B, L, 768, generator=g)
+    tmask = torch.ones(B, L, dtype=torch.bool)
+    pad = restate.mask_from_sizes(torch.tensor([250.0, 250.0, 199.0, 250.0, 120.0]))
+    ids, al = restate.process_anchors([[["+", 1.0, 3.0]], [], [], [["-", 0.0, 9.0]], []], pad, 1920, 48000)
+    time = torch.full((B,), 0.40625)
+    ref = restate.samaudio_forward(sd, cfg, noisy, feats, text, time, torch.zeros(B, 1024, T), tmask, ids, al, pad)
+    out = m.forward(noisy.cuda(), feats.cuda(), text.cuda(), time.cuda(), text_mask=tmask.cuda(),
+                    anchor_ids=ids.cuda(), anchor_alignment=al.cuda(), audio_pad_mask=pad.cuda())
+    assert rel_l2(out.cpu(), ref) < 2e-2
+
+
+def test_separate_full_clip_size_vs_oracle(small_model_and_sd):
+    """BASELINE clip size end to end (one 10 s @ 48 kHz clip, production-width model): codec encode, 2 midpoint steps
+    (4 evaluations; ode_opt is the reference's own knob), codec decode of target + residual, vs the CPU oracle."""
+    from oracle import restate
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_noise, synthetic_text_features
+    m, cfg, sd = small_model_and_sd
+    proc = SAMAudioProcessor(1920, 48000)
+    aud, desc = [synthetic_clip(3)], ["dog barking"]
+    host = proc(descriptions=desc, audios=aud)
+    noise = synthetic_noise(1, 250)
+    out = m.separate(proc(descriptions=desc, audios=aud).to("cuda"), noise=noise.cuda(),
+                     ode_opt={"method": "midpoint", "options": {"step_size": 0.5}})
+    tf, tm = synthetic_text_features(desc)
+    tgt, res = restate.separate(sd, cfg, host.audios, host.audio_pad_mask, host.sizes, tf, tm, host.anchor_ids,
+                                host.anchor_alignment, noise, n_steps=2)
+    assert out.target[0].shape == (480000,)
+    assert snr_db(out.target[0].cpu(), tgt[0]) > 30.0 and snr_db(out.residual[0].cpu(), res[0]) > 30.0
+
+
 def test_codec_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
     from oracle import restate
     from sam_audio_b200.synthetic import synthetic_clip
