@@ -107,6 +107,33 @@ int64_t sab_workspace_bytes(sab_engine* e);
 int sab_profile(sab_engine* e, int enable, void* stream);
 int sab_profile_report(sab_engine* e, char* json_out, int64_t capacity, void* stream);
 
+/* ---- T5 text encoder (SURVEY §8f-3 "next" row) ----
+ * replaces: the T5EncoderModel call inside T5TextEncoder.forward (reference sam_audio/model/text_encoder.py:29-35;
+ * HF transformers T5Stack arithmetic).  Tokenisation stays on the host (HF tokenizer, text_encoder.py:21-27).
+ * Weight names are the HF T5EncoderModel state-dict keys ("shared.weight",
+ * "encoder.block.N.layer.0.SelfAttention.q.weight", ...). */
+typedef struct sab_t5 sab_t5;
+typedef struct sab_t5_config {
+  int32_t vocab_size;   /* 32128 */
+  int32_t d_model;      /* 768   */
+  int32_t d_kv;         /* 64    */
+  int32_t d_ff;         /* 3072  */
+  int32_t n_layers;     /* 12    */
+  int32_t n_heads;      /* 12    */
+  int32_t n_buckets;    /* relative_attention_num_buckets = 32 */
+  float   eps;          /* layer_norm_epsilon = 1e-6 */
+} sab_t5_config;
+int sab_t5_create(const sab_t5_config* cfg, int device, sab_t5** out);
+int sab_t5_destroy(sab_t5* e);
+int sab_t5_load_weight(sab_t5* e, const char* name, const float* data, const int64_t* shape, int ndim, int is_device,
+                       void* stream);
+int sab_t5_finalize(sab_t5* e, void* stream);
+/* ids [B, L] int64, mask [B, L] uint8 (1 = token), rel_bucket [2L-1] int32 = T5's relative-position bucket of
+ * (key - query) + L - 1 (computed by the host exactly as transformers does); out [B, L, d_model] fp32. */
+int sab_t5_forward(sab_t5* e, const int64_t* ids, const uint8_t* mask, const int32_t* rel_bucket, int B, int L, float* out,
+                   void* stream);
+int64_t sab_t5_launch_count(sab_t5* e, int reset);
+
 /* ---- unit-test seams (used by tests/ only; stable but not part of the drop-in surface) ---- */
 /* C[M,N] (fp32) = A[M,K] (bf16) * B[N,K]^T (bf16) through the tcgen05 GEMM (tile BN x BK; cg = 1: one CTA per
  * 128-row tile, cg = 2: cta_group::2 pairs on 256-row tiles, cg = 0: the engine's default choice). */

@@ -30,10 +30,17 @@ class SabConfig(ctypes.Structure):
     ]
 
 
+class SabT5Config(ctypes.Structure):
+    _fields_ = [("vocab_size", ctypes.c_int32), ("d_model", ctypes.c_int32), ("d_kv", ctypes.c_int32),
+                ("d_ff", ctypes.c_int32), ("n_layers", ctypes.c_int32), ("n_heads", ctypes.c_int32),
+                ("n_buckets", ctypes.c_int32), ("eps", ctypes.c_float)]
+
+
 EXPORTS = [
     "sab_last_error", "sab_version", "sab_create", "sab_destroy", "sab_load_weight", "sab_finalize_weights",
     "sab_encode", "sab_prepare", "sab_dit_forward", "sab_solve", "sab_decode", "sab_launch_count",
     "sab_workspace_bytes", "sab_profile", "sab_profile_report", "sab_test_gemm", "sab_test_attention", "sab_test_attention_tc",
+    "sab_t5_create", "sab_t5_destroy", "sab_t5_load_weight", "sab_t5_finalize", "sab_t5_forward", "sab_t5_launch_count",
 ]
 
 
@@ -70,6 +77,13 @@ def lib() -> ctypes.CDLL:
         L.sab_test_gemm.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
         L.sab_test_attention.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         L.sab_test_attention_tc.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp]
+        L.sab_t5_create.argtypes = [ctypes.POINTER(SabT5Config), i32, ctypes.POINTER(vp)]
+        L.sab_t5_destroy.argtypes = [vp]
+        L.sab_t5_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, i32, vp]
+        L.sab_t5_finalize.argtypes = [vp, vp]
+        L.sab_t5_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+        L.sab_t5_launch_count.argtypes = [vp, i32]
+        L.sab_t5_launch_count.restype = i64
         _lib = L
     return _lib
 
@@ -170,3 +184,45 @@ class Engine:
 
     def workspace_bytes(self) -> int:
         return int(lib().sab_workspace_bytes(self._h))
+
+
+class T5Engine:
+    """Owns one sab_t5 handle (native T5 text encoder)."""
+
+    def __init__(self, hf_config, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("samaudio_b200: CUDA device required (no CPU fallback)")
+        c = SabT5Config()
+        c.vocab_size, c.d_model, c.d_kv, c.d_ff = hf_config.vocab_size, hf_config.d_model, hf_config.d_kv, hf_config.d_ff
+        c.n_layers, c.n_heads = hf_config.num_layers, hf_config.num_heads
+        c.n_buckets, c.eps = hf_config.relative_attention_num_buckets, hf_config.layer_norm_epsilon
+        self._cfg = c
+        self._h = ctypes.c_void_p()
+        check(lib().sab_t5_create(ctypes.byref(c), device, ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().sab_t5_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            t = v.detach().to(torch.float32).contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            check(lib().sab_t5_load_weight(self._h, k.encode(), t.data_ptr(), shape, t.dim(), 1 if t.is_cuda else 0,
+                                           stream_ptr()))
+        check(lib().sab_t5_finalize(self._h, stream_ptr()))
+
+    def forward(self, ids, mask_u8, rel_bucket, out):
+        B, L = ids.shape
+        check(lib().sab_t5_forward(self._h, ids.data_ptr(), mask_u8.data_ptr(), rel_bucket.data_ptr(), B, L,
+                                   out.data_ptr(), stream_ptr()))
+
+    def launch_count(self, reset=False) -> int:
+        return int(lib().sab_t5_launch_count(self._h, 1 if reset else 0))

@@ -1435,3 +1435,5 @@ int sab_test_attention_tc(int items, int heads, int T, const void* q, const void
 }
 
 }  // extern "C"
+
+#include "t5_engine.inc"

@@ -57,6 +57,7 @@ struct GemmParams {
   const float* bias; int bias_mod;           // bias[n % bias_mod] (bias_mod == 0: bias[n])
   const float* gate; int gate_ld; int gate_div;
   float alpha;
+  int relu;                                   // clamp at 0 after the residual add (T5 DenseReluDense)
   const float* res; long long res_ld;
   float* out_f32; long long out_f32_ld;
   __nv_bfloat16* out_bf16; long long out_bf16_ld;
@@ -368,6 +369,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int p = 0; p < 8; ++p) {
             x[p].x = fmaf(x[p].x, P.alpha, rr[p].x); x[p].y = fmaf(x[p].y, P.alpha, rr[p].y);
             x[p].z = fmaf(x[p].z, P.alpha, rr[p].z); x[p].w = fmaf(x[p].w, P.alpha, rr[p].w);
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              x[p].x = fmaxf(x[p].x, 0.f); x[p].y = fmaxf(x[p].y, 0.f); x[p].z = fmaxf(x[p].z, 0.f); x[p].w = fmaxf(x[p].w, 0.f);
+            }
           }
           if (P.out_f32) {
             float* o0 = P.out_f32 + row0 * P.out_f32_ld + n;

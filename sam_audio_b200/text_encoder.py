@@ -1,8 +1,11 @@
 """Text conditioning: T5 encoder wrapper (reference: sam_audio/model/text_encoder.py:11-37).
 
-T5-base is a third-party model (HF ``transformers``) that runs once per
-separate() call on a handful of tokens; it stays a PyTorch module feeding
-``sab_prepare`` (SURVEY.md §8a a5 / §8f-3 "next" row).  When no ``t5-base``
+Tokenisation stays on the host (HF tokenizer); on a B200 the encoder stack itself
+runs natively through ``sab_t5_forward`` (SURVEY.md §8a a5 / §8f-3 "next" row:
+T5LayerNorm, un-scaled attention with the bucketed relative-position bias and
+DenseReluDense on the same tcgen05 GEMM as the DiT), checked against
+``transformers.T5EncoderModel`` in tests/test_gpu_parity.py.  The HF module is kept
+only as the weight container (``from_pretrained`` / ``state_dict``); its forward is never called here.  When no ``t5-base``
 checkpoint/tokenizer is on disk (this sandbox has no network) the same module
 graph is built from the t5-base *shape* with seeded random weights and a
 deterministic hash tokenizer, so that benchmarks pay the real encoder cost on
@@ -12,9 +15,26 @@ from __future__ import annotations
 
 from typing import List, Tuple
 
+import math
+
 import torch
 
 from .config import T5EncoderConfig
+
+
+def t5_relative_buckets(L: int, num_buckets: int = 32, max_distance: int = 128) -> torch.Tensor:
+    """T5's bidirectional relative-position bucket of (key - query) for deltas -(L-1)..L-1, computed with the
+    same fp32 torch expression as transformers' T5Attention._relative_position_bucket so that boundary cases
+    round identically."""
+    rp = torch.arange(-(L - 1), L, dtype=torch.long)
+    nb = num_buckets // 2
+    buckets = (rp > 0).to(torch.long) * nb
+    rp = rp.abs()
+    max_exact = nb // 2
+    large = max_exact + (torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (nb - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    return (buckets + torch.where(rp < max_exact, rp, large)).to(torch.int32)
 
 
 class _HashTokenizer:
@@ -67,6 +87,20 @@ class T5TextEncoder(torch.nn.Module):
             self.tokenizer = _HashTokenizer(t5.vocab_size)
             self.random_init = True
         self.model.eval()
+        self._native = None
+        self._native_device = None
+
+    def _engine(self, device):
+        from . import _capi
+        if self._native is None or self._native_device != device:
+            if self._native is not None:
+                self._native.close()
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            with torch.cuda.device(idx):
+                self._native = _capi.T5Engine(self.model.config, idx)
+                self._native.load_state_dict(self.model.state_dict())
+            self._native_device = device
+        return self._native
 
     @torch.inference_mode()
     def forward(self, texts: List[str]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -75,7 +109,15 @@ class T5TextEncoder(torch.nn.Module):
                              return_tensors="pt")
         input_ids = enc["input_ids"].to(device)
         attention_mask = enc["attention_mask"].to(device)
-        hidden = self.model(input_ids=input_ids, attention_mask=attention_mask)["last_hidden_state"]
+        if device.type != "cuda":
+            raise RuntimeError("T5TextEncoder runs on a B200 only: move the model to cuda first (no CPU path)")
+        B, L = input_ids.shape
+        eng = self._engine(device)
+        cfg = self.model.config
+        buckets = t5_relative_buckets(L, cfg.relative_attention_num_buckets,
+                                      cfg.relative_attention_max_distance).to(device)
+        hidden = torch.empty(B, L, cfg.d_model, device=device, dtype=torch.float32)
+        eng.forward(input_ids.long().contiguous(), attention_mask.to(torch.uint8).contiguous(), buckets, hidden)
         return hidden, attention_mask.bool()
 
 

@@ -187,6 +187,28 @@ def test_separate_full_clip_size_vs_oracle(small_model_and_sd):
     assert snr_db(out.target[0].cpu(), tgt[0]) > 30.0 and snr_db(out.residual[0].cpu(), res[0]) > 30.0
 
 
+def test_native_t5_encoder_vs_transformers(capi):
+    """sab_t5_forward (tcgen05 GEMMs + relative-bias attention) vs transformers.T5EncoderModel with the same
+    random t5-base-shaped weights, ragged descriptions (padding mask) — tolerance as for one DiT evaluation."""
+    from sam_audio_b200.config import T5EncoderConfig
+    from sam_audio_b200.text_encoder import T5TextEncoder, t5_relative_buckets
+    enc = T5TextEncoder(T5EncoderConfig(), allow_random_init=True).cuda()
+    texts = ["man speaking", "a dog barking loudly in the distance near a busy street", "thunder", "car honking twice"]
+    ours, mask = enc(texts)
+    tok = enc.tokenizer(texts, truncation=True, max_length=512, padding="longest", return_tensors="pt")
+    ref = enc.model(input_ids=tok["input_ids"].cuda(), attention_mask=tok["attention_mask"].cuda())["last_hidden_state"]
+    assert torch.equal(mask.cpu(), tok["attention_mask"].bool()) and ours.shape == ref.shape
+    m = mask[..., None].float()
+    assert rel_l2(ours * m, ref * m) < 2e-2                 # padded positions carry no information
+    # bucket table = transformers' own function
+    from transformers.models.t5.modeling_t5 import T5Attention
+    L = 40
+    rp = torch.arange(L)[None, :] - torch.arange(L)[:, None]
+    hf = T5Attention._relative_position_bucket(rp, bidirectional=True, num_buckets=32, max_distance=128)
+    tab = t5_relative_buckets(L)
+    assert torch.equal(tab[(rp + L - 1)].long(), hf)
+
+
 def test_codec_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
     from oracle import restate
     from sam_audio_b200.synthetic import synthetic_clip
