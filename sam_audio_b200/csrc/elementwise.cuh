@@ -8,7 +8,7 @@ namespace sab {
 // ---------------------------------------------------------------------------------------------
 // RMSNorm + adaLN modulate  (transformer.py:42-47 RMSNorm fp32, :21-22 modulate, :375/:389/:513-515)
 //   out[m, :] = bf16( x[m,:] * rsqrt(mean(x^2)+eps) * w * (1 + scale[b,:]) + shift[b,:] ),  b = m / rows_per_item
-// one warp per row; the row stays in registers between the reduction and the write (single HBM read).
+// one warp per row.
 // ---------------------------------------------------------------------------------------------
 template <int kVecPerLane>  // d = kVecPerLane * 128
 __global__ void __launch_bounds__(256)
@@ -269,11 +269,6 @@ __global__ void rope_table_kernel(float2* __restrict__ rope, int T, int hd, floa
   const float inv = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
   const float a = (float)pos * inv;
   rope[idx] = make_float2(cosf(a), sinf(a));
-}
-
-// mask expansion helpers ------------------------------------------------------------------------
-__global__ void fill_kernel_f32(float* p, long long n, float v) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
 }  // namespace sab
