@@ -69,6 +69,8 @@ class SAMAudio(torch.nn.Module):
             text_encoder = T5TextEncoder(cfg.text_encoder, allow_random_init=allow_random_text_encoder)
         self.text_encoder = text_encoder
         self.vision_encoder = None      # PE-Core-L14 (third party) — SURVEY §8f-2 "next" row
+        # PE-A-Frame span predictor (third party, absent here): attach `span_predictor` + `span_predictor_transform`
+        # with the reference's call signatures (model.py:96-102) to enable predict_spans=True.
         self.visual_ranker = None       # rerankers are outside the hot path (default config: None)
         self.text_ranker = None
         self._engine: Optional[_capi.Engine] = None
@@ -217,8 +219,8 @@ class SAMAudio(torch.nn.Module):
             video = self.vision_encoder(batch.masked_video).transpose(1, 2)
         # reference behaviour: conditioning is fixed before span prediction; the
         # span predictor (PE-A-Frame, third party) only mutates `batch`.
-        if predict_spans and hasattr(self, "span_predictor") and batch.anchors is None:
-            batch = self.predict_spans(batch, feats, batch.audio_pad_mask)  # pragma: no cover
+        if predict_spans and getattr(self, "span_predictor", None) is not None and batch.anchors is None:
+            batch = self.predict_spans(batch, feats, batch.audio_pad_mask)
         self._install_conditioning(self._repeat(feats, c), self._repeat(text_features, c),
                                    self._repeat(text_mask, c), self._repeat(video, c),
                                    self._repeat(batch.anchor_ids, c), self._repeat(batch.anchor_alignment, c),
@@ -241,6 +243,17 @@ class SAMAudio(torch.nn.Module):
         idxs = [0] * B                                                      # model.py:329-330
         return SeparationResult(target=[w[i] for w, i in zip(tgt, idxs)],
                                 residual=[w[i] for w, i in zip(res, idxs)], noise=noise)
+
+    def predict_spans(self, batch: Batch, audio_features: torch.Tensor, audio_pad_mask: torch.Tensor) -> Batch:
+        """Reference model.py:231-245: frame-level span predictor on the first 128 latent channels -> "+" anchors ->
+        ``batch.process_anchors`` (mutates the caller's batch).  At the pinned reference commit the conditioning
+        has already been built from the old anchors, so the audio does not change."""
+        inputs = self.span_predictor_transform(text=batch.descriptions).to(audio_features.device)
+        output = self.span_predictor(input_features=audio_features[:, :, :128], padding_mask=audio_pad_mask,
+                                     return_spans=True, **inputs)
+        anchors = [[["+"] + list(a) for a in clip] for clip in output.spans]
+        batch.process_anchors(anchors)
+        return batch
 
     def unbatch(self, wavs: torch.Tensor, sizes: torch.Tensor, time_dim: int = -1):
         return [row.narrow(dim=time_dim, start=0, length=int(n)) for row, n in zip(wavs, sizes)]

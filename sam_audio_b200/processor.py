@@ -32,17 +32,20 @@ def _load_audio_file(path: str, sr: int) -> torch.Tensor:
 
 
 def batch_audio(audios: Sequence[AudioLike], audio_sampling_rate: int = 48_000):
-    """Channel-mean mono mix, right zero-pad to the longest clip -> ([B,1,S], lengths int64)."""
-    monos, pinned = [], len(audios) > 0
-    for a in audios:
-        w = _load_audio_file(a, audio_sampling_rate) if isinstance(a, str) else a
-        pinned = pinned and w.device.type == "cpu" and w.is_pinned()   # pinned in -> pinned batch out (async H2D)
-        monos.append(w.mean(0))
-    lengths = torch.tensor([m.size(-1) for m in monos])
-    longest = int(lengths.max()) if len(monos) else 0
-    out = torch.zeros(len(monos), 1, longest, dtype=monos[0].dtype, device=monos[0].device, pin_memory=pinned)
-    for i, m in enumerate(monos):
-        out[i, 0, : m.size(-1)] = m
+    """Channel-mean mono mix, right zero-pad to the longest clip -> ([B,1,S], lengths int64).
+    The mean is written straight into the padded batch (one pass over the samples); if every input is pinned the
+    batch is allocated pinned too, so ``Batch.to("cuda")`` is a single asynchronous copy."""
+    wavs = [_load_audio_file(a, audio_sampling_rate) if isinstance(a, str) else a for a in audios]
+    lengths = torch.tensor([w.size(-1) for w in wavs])
+    longest = int(lengths.max()) if len(wavs) else 0
+    pinned = len(wavs) > 0 and all(w.device.type == "cpu" and w.is_pinned() for w in wavs)
+    ref = wavs[0]
+    out = torch.zeros(len(wavs), 1, longest, dtype=ref.dtype, device=ref.device, pin_memory=pinned)
+    for i, w in enumerate(wavs):
+        if w.size(0) == 1:
+            out[i, 0, : w.size(-1)].copy_(w[0])          # mean over one channel is the channel itself (bit-exact)
+        else:
+            torch.mean(w, 0, out=out[i, 0, : w.size(-1)])
     return out, lengths
 
 

@@ -262,6 +262,38 @@ def test_separate_with_anchors_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
         assert ours.shape == ref.shape and snr_db(ours.cpu(), ref) > 30.0
 
 
+def test_predict_spans_mutates_batch_but_not_audio(tiny_model):
+    """Reference behaviour at the pinned commit (model.py:257-268): predicted spans are written into
+    the caller's batch (anchor ids / alignment, bit-exact integers) but the audio is that of the un-anchored batch."""
+    from types import SimpleNamespace
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_noise
+
+    class _Inputs(dict):
+        def to(self, device):
+            return self
+
+    class _FakeSpanPredictor:                     # stands in for core.audio_visual_encoder.PEAudioFrame
+        def __call__(self, input_features, padding_mask, return_spans, **kw):
+            assert input_features.shape[-1] == 128 and return_spans
+            return SimpleNamespace(spans=[[[0.02, 0.1]], [[0.0, 0.04], [0.06, 0.12]]])
+
+    proc = SAMAudioProcessor(1920, 48000)
+    auds = [synthetic_clip(20, 9600), synthetic_clip(21, 7000)]
+    noise = synthetic_noise(2, 5).cuda()
+    plain = tiny_model.separate(proc(descriptions=["a", "b"], audios=auds).to("cuda"), noise=noise)
+    tiny_model.span_predictor = _FakeSpanPredictor()
+    tiny_model.span_predictor_transform = lambda text: _Inputs()
+    try:
+        batch = proc(descriptions=["a", "b"], audios=auds).to("cuda")
+        out = tiny_model.separate(batch, noise=noise, predict_spans=True)
+    finally:
+        tiny_model.span_predictor = None
+    ref = proc(descriptions=["a", "b"], audios=auds, anchors=[[["+", 0.02, 0.1]], [["+", 0.0, 0.04], ["+", 0.06, 0.12]]])
+    assert torch.equal(batch.anchor_ids.cpu(), ref.anchor_ids) and torch.equal(batch.anchor_alignment.cpu(), ref.anchor_alignment)
+    assert all(torch.equal(a, b) for a, b in zip(out.target + out.residual, plain.target + plain.residual))
+
+
 def test_solver_composition_and_determinism(tiny_model):
     """sab_solve(n_steps=1) == the midpoint formula composed from two sab_dit_forward calls; repeated
     solves are bit-identical (no atomics / nondeterministic reductions on the path)."""
