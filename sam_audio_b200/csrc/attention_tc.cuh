@@ -1,7 +1,8 @@
 // tcgen05 self-attention for sequences of up to 256 keys (10 s clips: T = 250), head_dim = 128.
 // reference: sam_audio/model/transformer.py:153-160 (SDPA, scale 1/sqrt(hd), bool key mask, True = attend).
 //
-// One CTA = one (item, head): both 128-query tiles share one K/V load and run as two independent softmax
+// Persistent CTAs loop over (item, head) work items; the next item's Q/K (then V) tiles are prefetched as soon as
+// the tensor core has retired the MMAs that read them.  Per work item both 128-query tiles share one K/V load and run as two independent softmax
 // groups (warps 1-4 and 5-8, two warps per SM sub-partition) against one TMA/MMA issuing thread, so the second
 // tile's QK^T runs under the first tile's softmax and the first tile's PV under the second tile's softmax.
 // Everything between the two HBM touches stays on chip:
@@ -27,7 +28,7 @@ constexpr int ATC_SMEM = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES + 1024 /*barriers*/ 
 struct AttnTcParams {
   __nv_bfloat16* o; long long o_ld;
   const uint8_t* key_mask;          // [items, Tk] or null
-  int Tq, Tk, heads;
+  int Tq, Tk, heads, items;
   int q_col0, k_col0, v_col0;       // column of head 0 inside the fused QKV row
   float scale_log2;
   // debug knobs for bring-up of the MN-major V descriptor (bytes)
@@ -82,13 +83,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
   uint8_t* sV = sK + ATC_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATC_KV_BYTES);
   uint64_t *bar_q0k = bars, *bar_q1 = bars + 1, *bar_v = bars + 2;
-  uint64_t *bar_s = bars + 3 /*[2]*/, *bar_p = bars + 5 /*[2]*/, *bar_o = bars + 7 /*[2]*/;
+  uint64_t *bar_s = bars + 3 /*[2]*/, *bar_p = bars + 5 /*[2]*/, *bar_o = bars + 7 /*[2]*/, *bar_e = bars + 9 /*[2]*/;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  uint32_t* kmask = tmem_slot + 4;   // 8 words: bit j of word c = key c*32 + j may be attended
 
-  const int head = blockIdx.x, item = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_mt = (P.Tq + 127) / 128;             // 1 or 2 query tiles
+  const int n_work = P.heads * P.items;            // persistent CTAs loop over (item, head)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -102,20 +102,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
         mbar_init(bar_s + i, 1);
         mbar_init(bar_p + i, 128);
         mbar_init(bar_o + i, 1);
+        mbar_init(bar_e + i, 128);
       }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
-  } else if (warp == 1) {
-    // key validity bitmask (sequence end + padding mask)
-    const uint8_t* mk = P.key_mask ? P.key_mask + (long long)item * P.Tk : nullptr;
-    for (int c = 0; c < 8; ++c) {
-      const int key = c * 32 + lane;
-      const bool ok = key < P.Tk && (!mk || mk[key]);
-      const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) kmask[c] = bits;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -124,47 +116,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- loads: (Q0, K) first so the first QK^T can start, then Q1, then V ----
-      const int qc = P.q_col0 + head * 128, kc = P.k_col0 + head * 128, vc = P.v_col0 + head * 128;
-      mbar_expect_tx(bar_q0k, ATC_Q_BYTES + ATC_KV_BYTES);
-      tma_load_3d(sQ, &tm_q, bar_q0k, qc, 0, item);
-      tma_load_3d(sQ + ATC_Q_BYTES / 2, &tm_q, bar_q0k, qc + 64, 0, item);
-      tma_load_3d(sK, &tm_k, bar_q0k, kc, 0, item);
-      tma_load_3d(sK + ATC_KV_BYTES / 2, &tm_k, bar_q0k, kc + 64, 0, item);
-      if (n_mt > 1) {
-        mbar_expect_tx(bar_q1, ATC_Q_BYTES);
-        tma_load_3d(sQ + ATC_Q_BYTES, &tm_q, bar_q1, qc, 128, item);
-        tma_load_3d(sQ + ATC_Q_BYTES + ATC_Q_BYTES / 2, &tm_q, bar_q1, qc + 64, 128, item);
-      }
-      mbar_expect_tx(bar_v, ATC_KV_BYTES);
-      tma_load_3d(sV, &tm_v, bar_v, vc, 0, item);
-      tma_load_3d(sV + ATC_KV_BYTES / 2, &tm_v, bar_v, vc + 64, 0, item);
-      // ---- S_m = Q_m K^T  -> TMEM cols [256m, 256m + 256) ----
+      // (Q0, K) first so the first QK^T can start, then Q1; V separately (it is only needed for P V)
+      auto load_qk = [&](int w) {
+        const int head = w % P.heads, item = w / P.heads;
+        const int qc = P.q_col0 + head * 128, kc = P.k_col0 + head * 128;
+        mbar_expect_tx(bar_q0k, ATC_Q_BYTES + ATC_KV_BYTES);
+        tma_load_3d(sQ, &tm_q, bar_q0k, qc, 0, item);
+        tma_load_3d(sQ + ATC_Q_BYTES / 2, &tm_q, bar_q0k, qc + 64, 0, item);
+        tma_load_3d(sK, &tm_k, bar_q0k, kc, 0, item);
+        tma_load_3d(sK + ATC_KV_BYTES / 2, &tm_k, bar_q0k, kc + 64, 0, item);
+        if (n_mt > 1) {
+          mbar_expect_tx(bar_q1, ATC_Q_BYTES);
+          tma_load_3d(sQ + ATC_Q_BYTES, &tm_q, bar_q1, qc, 128, item);
+          tma_load_3d(sQ + ATC_Q_BYTES + ATC_Q_BYTES / 2, &tm_q, bar_q1, qc + 64, 128, item);
+        }
+      };
+      auto load_v = [&](int w) {
+        const int head = w % P.heads, item = w / P.heads;
+        const int vc = P.v_col0 + head * 128;
+        mbar_expect_tx(bar_v, ATC_KV_BYTES);
+        tma_load_3d(sV, &tm_v, bar_v, vc, 0, item);
+        tma_load_3d(sV + ATC_KV_BYTES / 2, &tm_v, bar_v, vc + 64, 0, item);
+      };
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 256);
-      for (int m = 0; m < n_mt; ++m) {
-        mbar_wait(m == 0 ? bar_q0k : bar_q1, 0);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t qa = smem_u32(sQ) + m * ATC_Q_BYTES + (ks >> 2) * (ATC_Q_BYTES / 2);
-          const uint32_t ka = smem_u32(sK) + (ks >> 2) * (ATC_KV_BYTES / 2);
-          umma_f16(tmem + m * 256, make_kmajor_desc<128>(qa) + (uint64_t)((ks & 3) * 2),
-                   make_kmajor_desc<128>(ka) + (uint64_t)((ks & 3) * 2), idesc_s, ks ? 1u : 0u);
-        }
-        umma_commit(bar_s + m);
-      }
-      // ---- O_m = P_m V  (A = P from TMEM cols [256m, +128), D = cols [256m + 128, +128)) ----
       constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 128);
-      mbar_wait(bar_v, 0);
-      for (int m = 0; m < n_mt; ++m) {
-        mbar_wait(bar_p + m, 0);
-        tc_fence_after();
+      if ((int)blockIdx.x < n_work) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int w_next = w + gridDim.x;
+        // ---- S_m = Q_m K^T  -> TMEM cols [256m, 256m + 256); the buffer is free once the previous item's
+        //      epilogue of tile m has read its O (which aliases the upper half of S_m) ----
+        for (int m = 0; m < n_mt; ++m) {
+          if (it > 0) mbar_wait(bar_e + m, ph ^ 1);
+          mbar_wait(m == 0 ? bar_q0k : bar_q1, ph);
+          tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {      // 16 keys per instruction
-          const uint64_t vb = make_mnmajor_desc(smem_u32(sV) + ks * 16 * 128, (uint32_t)P.v_lbo, (uint32_t)P.v_sbo);
-          umma_f16_ts(tmem + m * 256 + 128, tmem + m * 256 + ks * 8, vb, idesc_o, ks ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t qa = smem_u32(sQ) + m * ATC_Q_BYTES + (ks >> 2) * (ATC_Q_BYTES / 2);
+            const uint32_t ka = smem_u32(sK) + (ks >> 2) * (ATC_KV_BYTES / 2);
+            umma_f16(tmem + m * 256, make_kmajor_desc<128>(qa) + (uint64_t)((ks & 3) * 2),
+                     make_kmajor_desc<128>(ka) + (uint64_t)((ks & 3) * 2), idesc_s, ks ? 1u : 0u);
+          }
+          umma_commit(bar_s + m);
         }
-        umma_commit(bar_o + m);
+        // Q and K are dead once the last QK^T has retired: prefetch the next item's under this item's softmax
+        mbar_wait(bar_s + (n_mt - 1), ph);
+        if (w_next < n_work) load_qk(w_next);
+        // ---- O_m = P_m V  (A = P from TMEM cols [256m, +128), D = cols [256m + 128, +128)) ----
+        mbar_wait(bar_v, ph);
+        for (int m = 0; m < n_mt; ++m) {
+          mbar_wait(bar_p + m, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {      // 16 keys per instruction
+            const uint64_t vb = make_mnmajor_desc(smem_u32(sV) + ks * 16 * 128, (uint32_t)P.v_lbo, (uint32_t)P.v_sbo);
+            umma_f16_ts(tmem + m * 256 + 128, tmem + m * 256 + ks * 8, vb, idesc_o, ks ? 1u : 0u);
+          }
+          umma_commit(bar_o + m);
+        }
+        mbar_wait(bar_o + (n_mt - 1), ph);     // V is dead: prefetch the next item's
+        if (w_next < n_work) load_v(w_next);
       }
     }
   } else if (((warp - 1) >> 2) < n_mt) {
@@ -175,71 +187,88 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
     const int t = m * 128 + row;
     const uint32_t tS = tmem + m * 256 + ((uint32_t)(q * 32) << 16);
     const uint32_t tO = tS + 128;
-    mbar_wait(bar_s + m, 0);
-    tc_fence_after();
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      float v[32];
-      tmem_ld32(tS + c * 32, v);
-      tmem_ld_wait();
-      const uint32_t bits = kmask[c];
-      if (bits == 0xffffffffu) {
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int head = w % P.heads, item = w / P.heads;
+      // key validity bits of this item (sequence end + padding mask), one ballot per 32 keys
+      uint32_t kbits[8];
+      {
+        const uint8_t* mk = P.key_mask ? P.key_mask + (long long)item * P.Tk : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((bits >> j) & 1u) ? v[j] : -INFINITY);
-      }
-    }
-    const float mscaled = (mx == -INFINITY) ? 0.f : mx * P.scale_log2;
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      float v[32];
-      tmem_ld32(tS + c * 32, v);
-      tmem_ld_wait();
-      const uint32_t bits = kmask[c];
-      uint32_t pk[16];
-      if (bits == 0xffffffffu) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = ex2_approx(fmaf(v[j], P.scale_log2, -mscaled));
-          const float p1 = ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled));
-          sum += p0 + p1;
-          pk[j >> 1] = pack_bf16(p0, p1);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = ((bits >> j) & 1u) ? ex2_approx(fmaf(v[j], P.scale_log2, -mscaled)) : 0.f;
-          const float p1 = ((bits >> (j + 1)) & 1u) ? ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled)) : 0.f;
-          sum += p0 + p1;
-          pk[j >> 1] = pack_bf16(p0, p1);
+        for (int c = 0; c < 8; ++c) {
+          const int key = c * 32 + lane;
+          kbits[c] = __ballot_sync(0xffffffffu, key < P.Tk && (!mk || mk[key]));
         }
       }
-      tmem_st16(tS + c * 16, pk);   // in place: cols [16c, 16c+16) were consumed by chunk c/2 <= c
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(bar_p + m);
-    // ---- O / sum -> global ----
-    mbar_wait(bar_o + m, 0);
-    tc_fence_after();
-    const float inv = 1.f / sum;
-    __nv_bfloat16* op = P.o + ((long long)item * P.Tq + t) * P.o_ld + head * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
-      tmem_ld32(tO + c * 32, v);
-      tmem_ld_wait();
-      if (t < P.Tq) {
-        uint4* dst = reinterpret_cast<uint4*>(op + c * 32);
+      mbar_wait(bar_s + m, ph);
+      tc_fence_after();
+      float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(pack_bf16(v[8 * j] * inv, v[8 * j + 1] * inv), pack_bf16(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
-                              pack_bf16(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack_bf16(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
+      for (int c = 0; c < 8; ++c) {
+        float v[32];
+        tmem_ld32(tS + c * 32, v);
+        tmem_ld_wait();
+        const uint32_t bits = kbits[c];
+        if (bits == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((bits >> j) & 1u) ? v[j] : -INFINITY);
+        }
       }
+      const float mscaled = (mx == -INFINITY) ? 0.f : mx * P.scale_log2;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v[32];
+        tmem_ld32(tS + c * 32, v);
+        tmem_ld_wait();
+        const uint32_t bits = kbits[c];
+        uint32_t pk[16];
+        if (bits == 0xffffffffu) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(fmaf(v[j], P.scale_log2, -mscaled));
+            const float p1 = ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled));
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ((bits >> j) & 1u) ? ex2_approx(fmaf(v[j], P.scale_log2, -mscaled)) : 0.f;
+            const float p1 = ((bits >> (j + 1)) & 1u) ? ex2_approx(fmaf(v[j + 1], P.scale_log2, -mscaled)) : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+        }
+        tmem_st16(tS + c * 16, pk);   // in place: cols [16c, 16c+16) were consumed by chunk c/2 <= c
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p + m);
+      // ---- O / sum -> global ----
+      mbar_wait(bar_o + m, ph);
+      tc_fence_after();
+      const float inv = 1.f / sum;
+      __nv_bfloat16* op = P.o + ((long long)item * P.Tq + t) * P.o_ld + head * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(tO + c * 32, v);
+        tmem_ld_wait();
+        if (t < P.Tq) {
+          uint4* dst = reinterpret_cast<uint4*>(op + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16(v[8 * j] * inv, v[8 * j + 1] * inv), pack_bf16(v[8 * j + 2] * inv, v[8 * j + 3] * inv),
+                                pack_bf16(v[8 * j + 4] * inv, v[8 * j + 5] * inv), pack_bf16(v[8 * j + 6] * inv, v[8 * j + 7] * inv));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_e + m);   // S_m / O_m may be overwritten by the next item's QK^T
     }
   }
   tc_fence_before();

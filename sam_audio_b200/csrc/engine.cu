@@ -687,8 +687,10 @@ static void launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, co
     SAB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
     configured = true;
   }
-  dim3 grid(ap.heads, items);
-  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, st>>>(tq, tk, tv, ap);
+  AttnTcParams p2 = ap;
+  p2.items = items;
+  const int n_work = ap.heads * items;
+  attention_tc_kernel<<<n_work < g_sm_count ? n_work : g_sm_count, ATC_THREADS, ATC_SMEM, st>>>(tq, tk, tv, p2);
   SAB_CUDA(cudaGetLastError());
 }
 
@@ -1420,6 +1422,11 @@ int sab_test_attention_tc(int items, int heads, int T, const void* q, const void
                           const uint8_t* key_mask, void* o, int v_lbo, int v_sbo, void* stream) {
   SAB_API_BEGIN
   SAB_CHECK(T <= 256, "tcgen05 attention handles T <= 256");
+  if (!g_sm_count) {
+    cudaDeviceProp prop;
+    SAB_CUDA(cudaGetDeviceProperties(&prop, 0));
+    g_sm_count = prop.multiProcessorCount;
+  }
   const long long ld = (long long)heads * 128;
   CUtensorMap tq = make_tmap_3d(q, ld, T, items, ld, (int64_t)T * ld, 64, 128);
   CUtensorMap tk = make_tmap_3d(k, ld, T, items, ld, (int64_t)T * ld, 64, 256);

@@ -217,14 +217,16 @@ class SAMAudio(torch.nn.Module):
                 raise NotImplementedError("visual prompting needs the PE-Core vision encoder "
                                           "(third-party; SURVEY §8f-2) — attach one as model.vision_encoder")
             video = self.vision_encoder(batch.masked_video).transpose(1, 2)
-        # reference behaviour: conditioning is fixed before span prediction; the
-        # span predictor (PE-A-Frame, third party) only mutates `batch`.
+        # reference behaviour (model.py:257-268): the forward arguments (anchor tensors included)
+        # are bound BEFORE span prediction; predict_spans rebinds batch.anchor_ids/alignment afterwards, so the
+        # predicted spans reach the caller's batch but not this call's audio.
+        anchor_ids, anchor_alignment, pad_mask = batch.anchor_ids, batch.anchor_alignment, batch.audio_pad_mask
         if predict_spans and getattr(self, "span_predictor", None) is not None and batch.anchors is None:
             batch = self.predict_spans(batch, feats, batch.audio_pad_mask)
         self._install_conditioning(self._repeat(feats, c), self._repeat(text_features, c),
                                    self._repeat(text_mask, c), self._repeat(video, c),
-                                   self._repeat(batch.anchor_ids, c), self._repeat(batch.anchor_alignment, c),
-                                   self._repeat(batch.audio_pad_mask, c))
+                                   self._repeat(anchor_ids, c), self._repeat(anchor_alignment, c),
+                                   self._repeat(pad_mask, c))
         if noise is None:
             noise = torch.randn(B * c, T, C2, device=feats.device, dtype=torch.float32)
         noise = noise.to(device=feats.device, dtype=torch.float32).contiguous()

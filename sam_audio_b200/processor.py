@@ -90,7 +90,7 @@ class Batch:
         n = len(self.audios)
         frames = self.audio_pad_mask.size(-1)
         alignment = torch.zeros(n, frames, dtype=torch.long)
-        alignment[~self.audio_pad_mask] = 1
+        alignment[~self.audio_pad_mask.cpu()] = 1         # host tensor: the batch may already live on the GPU
         if anchors is None:
             ids = torch.tensor([[_ANCHOR_IDS["<null>"], _ANCHOR_IDS["<pad>"]]], dtype=torch.long).repeat(n, 1)
         else:
