@@ -27,17 +27,17 @@ static int g_sm_count = 0;
 // =====================================================================================================
 // GEMM dispatch
 // =====================================================================================================
-template <int BN, int BK, int MODE, int CG>
+template <int BN, int BK, int MODE, int CG, bool B2B = false>
 static void launch_gemm_inst(const GemmOp& op, cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, BK, MODE, CG>;
-  constexpr int smem = GemmSmem<BN, BK, CG>::kTotal;
+  auto kern = gemm_tc_kernel<BN, BK, MODE, CG, B2B>;
+  constexpr int smem = GemmSmem<BN, BK, CG, B2B>::kTotal;
   if (!configured) {
     SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   if (CG == 1) {
-    kern<<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, op.P);
+    kern<<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, op.b2b ? op.tmW : op.tmB, op.P);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(op.grid);
@@ -51,12 +51,18 @@ static void launch_gemm_inst(const GemmOp& op, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SAB_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.P));
+    SAB_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmB, op.P));
   }
   SAB_CUDA(cudaGetLastError());
 }
 
 static void launch_gemm(const GemmOp& op, cudaStream_t st) {
+  if (op.b2b) {
+    if (op.BN == 64 && op.BK == 64) return launch_gemm_inst<64, 64, EPI_AFFINE, 1, true>(op, st);
+    if (op.BN == 96 && op.BK == 32) return launch_gemm_inst<96, 32, EPI_AFFINE, 1, true>(op, st);
+    if (op.BN == 128 && op.BK == 64) return launch_gemm_inst<128, 64, EPI_AFFINE, 1, true>(op, st);
+    throw Error(fmt("no back-to-back GEMM instantiation for BN=%d BK=%d (%s)", op.BN, op.BK, op.tag));
+  }
 #define SAB_CASE(bn_, bk_, md_, cg_) \
   if (op.BN == bn_ && op.BK == bk_ && op.mode == md_ && op.cg == cg_) return launch_gemm_inst<bn_, bk_, md_, cg_>(op, st);
   SAB_CASE(256, 64, EPI_AFFINE, 2)
@@ -820,9 +826,31 @@ static int pick_bk(int cin) {
 struct StageBufs { float* x; bf16* a; bf16* mid; };
 
 // Conv1d(c, c, k=7, dilation) 'same' + Snake  ->  Conv1d(c, c, 1) + residual  (+ Snake for the consumer)
-static void plan_resunit(CodecPlan& cp, const ResUnitW& R, int items, long long Tn, int C, const StageBufs& sb,
+// C <= 128: ONE launch — the 1x1 conv runs back to back on the tensor core from the activated tile in shared
+// memory (the intermediate never touches HBM); its output goes to the other operand buffer (sb.a / sb.mid swap)
+// because neighbouring tiles still read this unit's input through their dilated taps.
+static void plan_resunit(CodecPlan& cp, const ResUnitW& R, int items, long long Tn, int C, StageBufs& sb,
                          const float* next_alpha, bool keep_x) {
   const int bk = pick_bk(C), bn = pick_bn(C);
+  static const bool no_b2b = getenv("SAB_NO_B2B") != nullptr;
+  if (C <= 128 && bn == C && !no_b2b) {
+    RunList rl;
+    for (int k = 0; k < 7; ++k) rl.add(0, (k - 3) * R.c7.dil, 0, C / bk);
+    CodecStep s;
+    s.op = make_gemm(cp.tag(fmt("codec.res.b2b.c%d", C)), seq_view(sb.a, items, Tn, C), R.c7.w, C, bn, bk, EPI_AFFINE, rl, 1);
+    s.op.b2b = true;
+    s.op.tmW = make_tmap_2d(R.c1.w, C, C, C, bk, bn);
+    s.op.P.b2b_bias = R.c7.bias; s.op.P.b2b_alpha = R.a1;
+    s.op.P.bias = R.c1.bias;
+    s.op.P.res = sb.x; s.op.P.res_ld = C;
+    if (keep_x) { s.op.P.out_f32 = sb.x; s.op.P.out_f32_ld = C; }
+    s.op.P.out_act = sb.mid; s.op.P.out_act_ld = C; s.op.P.snake_alpha = next_alpha;
+    s.op.flops += 2.0 * items * (double)Tn * C * C;
+    cp.flops += s.op.flops;
+    cp.steps.push_back(s);
+    std::swap(sb.a, sb.mid);
+    return;
+  }
   {
     RunList rl;
     for (int k = 0; k < 7; ++k) rl.add(0, (k - 3) * R.c7.dil, 0, C / bk);

@@ -62,6 +62,8 @@ struct GemmParams {
   float* out_f32; long long out_f32_ld;
   __nv_bfloat16* out_bf16; long long out_bf16_ld;
   __nv_bfloat16* out_act; long long out_act_ld; const float* snake_alpha;  // snake_alpha[n % bias_mod]
+  // back-to-back mode: acc1 = Snake_{b2b_alpha}(acc0 + b2b_bias) @ W1^T, then the affine epilogue runs on acc1
+  const float* b2b_bias; const float* b2b_alpha;
   // qkv epilogue
   const float* qnorm_w; const float* knorm_w;  // [128]
   int n_q_end, n_k_end;                        // cols [0,n_q_end): q-norm, [n_q_end,n_k_end): k-norm, rest plain
@@ -74,7 +76,7 @@ struct GemmParams {
 };
 constexpr int XA_MAX_TK = 8;
 
-template <int BN, int BK, int CG>
+template <int BN, int BK, int CG, bool B2B = false>
 struct GemmSmem {
   static constexpr int kABytes = GEMM_BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;
@@ -82,9 +84,13 @@ struct GemmSmem {
   static constexpr int kStageLd = 36;                          // fp32 words per staged row (32 + 4 pad)
   static constexpr int kEpiBytes = 8 * 32 * kStageLd * 4;      // 8 epilogue warps x 32 rows
   static constexpr int kBarBytes = 1024;
-  static constexpr int kBudget = 227 * 1024 - kEpiBytes - kBarBytes - 1024;
+  // back-to-back second GEMM (1x1 conv of a residual unit): its [BN x BN] weight stays resident and the activated
+  // 128 x BN intermediate tile is handed to the tensor core through shared memory, both K-major swizzled
+  static constexpr int kW1Bytes = B2B ? BN * BN * 2 : 0;
+  static constexpr int kMidBytes = B2B ? GEMM_BM * BN * 2 : 0;
+  static constexpr int kBudget = 227 * 1024 - kEpiBytes - kBarBytes - 1024 - kW1Bytes - kMidBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: manual alignment
+  static constexpr int kTotal = kStages * kStageBytes + kW1Bytes + kMidBytes + kBarBytes + kEpiBytes + 1024;  // +1024: alignment
 };
 
 // ---- cluster helpers (CG = 2) ----
@@ -156,11 +162,13 @@ SAB_DEVICE void tile_coords(int tile, int n_tiles_m, int n_tiles_n, int group_m,
 
 SAB_DEVICE uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
 
-template <int BN, int BK, int MODE, int CG>
+template <int BN, int BK, int MODE, int CG, bool B2B = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmW /*B2B: [BN, BN] second weight, box BK x BN*/,
                const __grid_constant__ GemmParams P) {
-  using S = GemmSmem<BN, BK, CG>;
+  using S = GemmSmem<BN, BK, CG, B2B>;
+  static_assert(!B2B || (CG == 1 && MODE == EPI_AFFINE && BN <= 128), "back-to-back mode: 1-CTA affine tiles, N <= 128");
   constexpr int kStages = S::kStages;
   constexpr int kLd = S::kStageLd;
   constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -173,12 +181,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + kStages * S::kStageBytes;
+  uint8_t* s_w1 = smem + kStages * S::kStageBytes;            // [BN/BK chunks][BN rows x BK] (B2B)
+  uint8_t* s_mid = s_w1 + S::kW1Bytes;                         // [BN/BK chunks][128 rows x BK] (B2B)
+  uint8_t* bar_base = s_mid + S::kMidBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b2b_full = tmem_empty + 2;      // [2] second GEMM retired into accumulator a
+  uint64_t* mid_ready = b2b_full + 2;       // all epilogue warps have written the intermediate tile
+  uint64_t* w1_bar = mid_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_bar + 1);
   float* epi_stage = reinterpret_cast<float*>(bar_base + S::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -201,7 +214,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8 * CG);  // one arrive per epilogue warp of every CTA of the group
+      mbar_init(&b2b_full[a], 1);
     }
+    mbar_init(mid_ready, 8);
+    mbar_init(w1_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -216,6 +232,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
+      if constexpr (B2B) {   // the second GEMM's weight: loaded once, resident for the CTA's lifetime
+        mbar_expect_tx(w1_bar, S::kW1Bytes);
+        for (int kc = 0; kc < BN / BK; ++kc) tma_load_2d(s_w1 + kc * (BN * BK * 2), &tmW, w1_bar, kc * BK, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit; tile < n_tiles; tile += n_units) {
@@ -255,6 +275,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // back-to-back: the second GEMM of tile i is issued as soon as the epilogue warps have published the
+      // activated intermediate tile — polled between the k-blocks of tile i+1, at the latest before tile i+1 commits
+      int pend_acc = -1;
+      uint32_t mid_phase = 0;
+      bool w1_loaded = false;
+      auto issue_b2b = [&](int a) {
+        if (!w1_loaded) { mbar_wait(w1_bar, 0); w1_loaded = true; }
+        tc_fence_after();
+        const uint32_t d2 = tmem_base + a * kAccStride;
+#pragma unroll
+        for (int kc = 0; kc < BN / BK; ++kc) {
+          const uint64_t dm = make_kmajor_desc<BK * 2>(smem_u32(s_mid + kc * (GEMM_BM * BK * 2)));
+          const uint64_t dw = make_kmajor_desc<BK * 2>(smem_u32(s_w1 + kc * (BN * BK * 2)));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(d2, dm + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        }
+        umma_commit(&b2b_full[a]);
+      };
       for (int tile = unit; tile < n_tiles; tile += n_units) {
         int mt, nt;
         tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
@@ -266,6 +304,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < total_kb; ++kb) {
+          if constexpr (B2B) {
+            if (pend_acc >= 0 && mbar_try_wait(mid_ready, mid_phase)) { issue_b2b(pend_acc); pend_acc = -1; mid_phase ^= 1; }
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
@@ -281,8 +322,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if constexpr (B2B) {
+          if (pend_acc >= 0) { mbar_wait(mid_ready, mid_phase); issue_b2b(pend_acc); pend_acc = -1; mid_phase ^= 1; }
+        }
         if constexpr (CG == 2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+        if constexpr (B2B) pend_acc = acc;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if constexpr (B2B) {
+        if (pend_acc >= 0) { mbar_wait(mid_ready, mid_phase); issue_b2b(pend_acc); }
       }
     }
   } else if (warp >= 4) {
@@ -338,9 +386,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int p = 0; p < 8; ++p)
             goff[p] = (4 * p < rl) ? (long long)((int)(row0 + 4 * p) / P.gate_div) * P.gate_ld : 0;
         }
-        load_res(half * 32, rr);
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
+        if constexpr (B2B) {
+          // ---- first epilogue: Snake(acc0 + bias) -> bf16 -> the K-major swizzled A tile of the second GEMM ----
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const int r_tile = q * 32 + lane;                    // row of this thread inside the 128-row tile
+#pragma unroll 1
+          for (int c = half * 32; c < BN; c += 64) {
+            float v[32];
+            tmem_ld32(t_addr + c, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.b2b_bias + c + j));
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.b2b_alpha + c + j));
+              float x0 = v[j] + b4.x, x1 = v[j + 1] + b4.y, x2 = v[j + 2] + b4.z, x3 = v[j + 3] + b4.w, sn;
+              sn = __sinf(a4.x * x0); x0 = fmaf(sn * sn, 1.f / (a4.x + 1e-9f), x0);
+              sn = __sinf(a4.y * x1); x1 = fmaf(sn * sn, 1.f / (a4.y + 1e-9f), x1);
+              sn = __sinf(a4.z * x2); x2 = fmaf(sn * sn, 1.f / (a4.z + 1e-9f), x2);
+              sn = __sinf(a4.w * x3); x3 = fmaf(sn * sn, 1.f / (a4.w + 1e-9f), x3);
+              pk[j >> 1] = pack_bf16(x0, x1);
+              pk[(j >> 1) + 1] = pack_bf16(x2, x3);
+            }
+            // chunk of BK columns kc, 16-byte unit u inside the row, XOR-swizzled like the TMA/UMMA layout
+            uint8_t* tile = s_mid + (c / BK) * (GEMM_BM * BK * 2) + r_tile * (BK * 2);
+            const int u0 = (c % BK) / 8;
+            const int sw = (BK == 64) ? (r_tile & 7) : ((r_tile >> 1) & 3);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(tile + (((u0 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(mid_ready);
+          load_res(half * 32, rr);
+          mbar_wait(&b2b_full[acc], acc_phase);
+          tc_fence_after();
+        } else {
+          load_res(half * 32, rr);
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+        }
 #pragma unroll 1
         for (int c = half * 32; c < BN; c += 64) {
           if (n0 + c >= P.N) break;

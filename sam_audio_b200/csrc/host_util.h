@@ -122,9 +122,10 @@ inline CUtensorMap make_tmap_2d(const void* base, int64_t cols, int64_t rows, in
 
 // ---- a planned GEMM launch ----
 struct GemmOp {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmW;   // tmW: resident second weight of a back-to-back pair (b2b)
   GemmParams P;
   int BN = 0, BK = 64, mode = EPI_AFFINE, cg = 1;
+  bool b2b = false;
   int grid = 0;
   const char* tag = "";
   double flops = 0;  // algorithmic 2*M*N*K
