@@ -131,6 +131,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);// m_dim
 }
 
+// explicit shared-window accesses (a pointer carved out of `extern __shared__` by byte arithmetic is a generic
+// pointer to the compiler: it would emit LD.E/ST.E with an address-space check instead of LDS/STS)
+SAB_DEVICE void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+SAB_DEVICE void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SAB_DEVICE float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------- math / packing
 SAB_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
 SAB_DEVICE uint32_t pack_bf16(float a, float b) {

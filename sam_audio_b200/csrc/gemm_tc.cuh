@@ -340,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int e = warp - 4;                    // 0..7
     const int q = e & 3;                       // TMEM lane quarter (== warp % 4)
     const int half = e >> 2;                   // which alternating 32-column chunks this warp owns
-    float* stg = epi_stage + e * 32 * kLd;     // this warp's staging tile
+    const uint32_t stg = smem_u32(epi_stage) + (uint32_t)(e * 32 * kLd * 4);   // this warp's staging tile (shared window)
     const int tr_r = lane >> 3;                // transposed mapping: pass p covers row 4p + tr_r,
     const int tr_c = (lane & 7) * 4;           //   4 consecutive columns tr_c .. tr_c+3
     int acc = 0;
@@ -357,14 +357,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       // write this thread's 32 accumulator values (one row) into the staging tile, then read them back transposed
       auto stage_put = [&](const float (&v)[32]) {
-        float4* dst = reinterpret_cast<float4*>(stg + lane * kLd);
+        const uint32_t dst = stg + (uint32_t)(lane * kLd * 4);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) sts128(dst + 16 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         __syncwarp();
       };
       auto stage_get = [&](float4 (&x)[8]) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) x[p] = *reinterpret_cast<const float4*>(stg + (4 * p + tr_r) * kLd + tr_c);
+        for (int p = 0; p < 8; ++p) x[p] = lds128(stg + (uint32_t)(((4 * p + tr_r) * kLd + tr_c) * 4));
       };
 
       if constexpr (MODE == EPI_AFFINE) {
@@ -410,12 +410,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               pk[(j >> 1) + 1] = pack_bf16(x2, x3);
             }
             // chunk of BK columns kc, 16-byte unit u inside the row, XOR-swizzled like the TMA/UMMA layout
-            uint8_t* tile = s_mid + (c / BK) * (GEMM_BM * BK * 2) + r_tile * (BK * 2);
+            const uint32_t tile = smem_u32(s_mid) + (uint32_t)((c / BK) * (GEMM_BM * BK * 2) + r_tile * (BK * 2));
             const int u0 = (c % BK) / 8;
             const int sw = (BK == 64) ? (r_tile & 7) : ((r_tile >> 1) & 3);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<uint4*>(tile + (((u0 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              sts128u(tile + (uint32_t)(((u0 + u) ^ sw) << 4), make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]));
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
           tc_fence_before();
