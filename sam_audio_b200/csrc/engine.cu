@@ -239,6 +239,8 @@ struct sab_engine {
   // --- DiT weights ---
   std::vector<LayerW> layers;
   float* tables = nullptr;          // [L, 6, d]
+  bf16* wkv_c_all = nullptr;        // [L, 2d, d]
+  float* kn_c_all = nullptr;        // [L, 128]
   bf16 *wp_y, *wp_f, *wmem, *wvid;  // proj (noisy third / feature third), memory_proj, align conv
   float *proj_b, *mem_b, *vid_b, *vid_ln_w, *vid_ln_b, *vid_gate, *vid_const;
   float *anchor_embed, *anchor_proj, *anchor_gate, *anchor_table;
@@ -405,6 +407,8 @@ static void register_weights(sab_engine* e) {
   reg_f32(e, "transformer.final_layer_scale_shift_table", {2, d}, &e->final_table);
   // ---- DiT layers ----
   e->tables = e->wpool.alloc<float>((int64_t)L * 6 * d, true);
+  e->wkv_c_all = e->wpool.alloc<bf16>((int64_t)L * 2 * d * d, true);   // all layers' cross wk|wv: one GEMM per evaluation
+  e->kn_c_all = e->wpool.alloc<float>((int64_t)L * 128, true);
   e->layers.resize(L);
   for (int l = 0; l < L; ++l) {
     LayerW& W = e->layers[l];
@@ -417,12 +421,18 @@ static void register_weights(sab_engine* e) {
     reg_f32(e, p + ".attention.q_norm.weight", {128}, &W.qn);
     reg_f32(e, p + ".attention.k_norm.weight", {128}, &W.kn);
     reg_linear(e, p + ".cross_attention.wq.weight", d, d, &W.wq_c, ROW_HEADS, H);
-    W.wkv_c = e->wpool.alloc<bf16>((int64_t)2 * d * d, true);
+    W.wkv_c = e->wkv_c_all + (int64_t)l * 2 * d * d;
     reg_linear(e, p + ".cross_attention.wk.weight", d, d, nullptr, ROW_HEADS, H, W.wkv_c, 0, d);
     reg_linear(e, p + ".cross_attention.wv.weight", d, d, nullptr, ROW_HEADS, H, W.wkv_c, d, d);
     reg_linear(e, p + ".cross_attention.wo.weight", d, d, &W.wo_c);
     reg_f32(e, p + ".cross_attention.q_norm.weight", {128}, &W.qn_c);
-    reg_f32(e, p + ".cross_attention.k_norm.weight", {128}, &W.kn_c);
+    W.kn_c = e->kn_c_all + (int64_t)l * 128;
+    {
+      float* dst = W.kn_c;
+      reg(e, p + ".cross_attention.k_norm.weight", {128}, [dst](const float* src, cudaStream_t st) {
+        SAB_CUDA(cudaMemcpyAsync(dst, src, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      });
+    }
     W.w13 = e->wpool.alloc<bf16>((int64_t)2 * hid * d, true);
     reg_linear(e, p + ".feed_forward.w1.weight", hid, d, nullptr, ROW_SWIGLU_A, 1, W.w13, 0, d);
     reg_linear(e, p + ".feed_forward.w3.weight", hid, d, nullptr, ROW_SWIGLU_B, 1, W.w13, 0, d);
@@ -512,7 +522,7 @@ struct DitPlan {
   long long *anchor_ids, *anchor_align;
   int n_ids_cap = 0;
   // ops
-  GemmOp g_t13, g_t2, g_tb, g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid;
+  GemmOp g_t13, g_t2, g_tb, g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid, g_kvc_all;
   std::vector<LayerOps> lay;
   CUtensorMap tm_att_q, tm_att_kv;   // fused-QKV buffer viewed as (3d cols, T rows, Bc items): box 64x128 / 64x256
   bool att_tc = false;               // tcgen05 self-attention usable (T <= 256)
@@ -547,7 +557,7 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
   p.time_dev = w.alloc<float>((int64_t)Bc * 64);
   p.y_bf = w.alloc<bf16>(M * 256); p.gn_a = w.alloc<bf16>(M * d); p.hb = w.alloc<bf16>(M * d);
   p.xn = w.alloc<bf16>(M * d); p.qkv = w.alloc<bf16>(M * 3 * d); p.att = w.alloc<bf16>(M * d);
-  p.qc = w.alloc<bf16>(M * d); p.kvc = w.alloc<bf16>(ML * 2 * d); p.u = w.alloc<bf16>(M * hid);
+  p.qc = w.alloc<bf16>(M * d); p.kvc = w.alloc<bf16>(ML * 2 * d * NL); p.u = w.alloc<bf16>(M * hid);
   p.tfreq = w.alloc<bf16>((int64_t)Bc * 256); p.t_h = w.alloc<bf16>((int64_t)Bc * d);
   p.t_silu = w.alloc<bf16>((int64_t)Bc * d);
   p.mem_in = w.alloc<bf16>(ML * d); p.y_h = w.alloc<bf16>(ML * d); p.ymem = w.alloc<bf16>(ML * d);
@@ -595,6 +605,8 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
     const LayerW& W = e->layers[l];
     LayerOps& o = p.lay[l];
     float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
+    const long long kv_ld = 2LL * d * NL;            // layer l's K|V live at columns [l*2d, (l+1)*2d) of p.kvc
+    bf16* kvc_l = p.kvc + (long long)l * 2 * d;
     o.qkv = make_linear("attention.qkv", p.xn, M, d, W.wqkv, 3 * d, 256, EPI_QKV);
     o.qkv.P.out_bf16 = p.qkv; o.qkv.P.out_bf16_ld = 3 * d;
     o.qkv.P.qnorm_w = W.qn; o.qkv.P.knorm_w = W.kn; o.qkv.P.n_q_end = d; o.qkv.P.n_k_end = 2 * d;
@@ -611,15 +623,12 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
       SAB_CHECK(o.q_c.BN == 256, "fused cross-attention needs BN=256 tiles");
       o.q_c.tag = "cross.wq+attn";
       o.q_c.P.out_bf16 = p.att; o.q_c.P.out_bf16_ld = d;
-      o.q_c.P.xa_kv = p.kvc; o.q_c.P.xa_kv_ld = 2 * d; o.q_c.P.xa_v_col0 = d; o.q_c.P.xa_Tk = L; o.q_c.P.xa_T = T;
+      o.q_c.P.xa_kv = kvc_l; o.q_c.P.xa_kv_ld = kv_ld; o.q_c.P.xa_v_col0 = d; o.q_c.P.xa_Tk = L; o.q_c.P.xa_T = T;
       o.q_c.P.xa_mask = p.text_mask;
       o.q_c.P.xa_scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
       o.q_c.flops += 4.0 * Bc * c.n_heads * (double)T * L * 128;
     }
-    o.kv_c = make_linear("cross.wkv", p.ymem, ML, d, W.wkv_c, 2 * d, 256, EPI_QKV);
-    o.kv_c.P.out_bf16 = p.kvc; o.kv_c.P.out_bf16_ld = 2 * d;
-    o.kv_c.P.qnorm_w = W.qn_c; o.kv_c.P.knorm_w = W.kn_c; o.kv_c.P.n_q_end = 0; o.kv_c.P.n_k_end = d;
-    o.kv_c.P.rope_T = L; o.kv_c.P.use_rope = 0; o.kv_c.P.eps = c.norm_eps;
+
     o.wo_c = make_linear("cross.wo", p.att, M, d, W.wo_c, d, 256, EPI_AFFINE);
     o.wo_c.P.res = p.h; o.wo_c.P.res_ld = d; o.wo_c.P.out_f32 = p.h; o.wo_c.P.out_f32_ld = d;
     o.w13 = make_linear("ffn.w13", p.xn, M, d, W.w13, 2 * hid, 256, EPI_SWIGLU);
@@ -629,6 +638,12 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
     o.w2.P.res = p.h; o.w2.P.res_ld = d; o.w2.P.out_f32 = p.h; o.w2.P.out_f32_ld = d;
   }
   p.g_out = make_linear("output", p.xn, M, d, e->w_out, c.out_channels, 256, EPI_AFFINE);
+  // every layer's text K|V in one GEMM per evaluation: [Bc*L, d] x [NL*2d, d]^T, k-norm per layer
+  p.g_kvc_all = make_linear("cross.wkv(all layers)", p.ymem, ML, d, e->wkv_c_all, 2 * d * NL, 256, EPI_QKV);
+  p.g_kvc_all.P.out_bf16 = p.kvc; p.g_kvc_all.P.out_bf16_ld = 2LL * d * NL;
+  p.g_kvc_all.P.qnorm_w = e->kn_c_all; p.g_kvc_all.P.knorm_w = e->kn_c_all;
+  p.g_kvc_all.P.n_q_end = 0; p.g_kvc_all.P.n_k_end = d; p.g_kvc_all.P.qkv_period = 2 * d; p.g_kvc_all.P.norm_w_stride = 128;
+  p.g_kvc_all.P.rope_T = L; p.g_kvc_all.P.use_rope = 0; p.g_kvc_all.P.eps = c.norm_eps;
   p.att_tc = (T <= 256) && !getenv("SAB_NO_TC_ATTENTION");
   if (p.att_tc) {
     p.tm_att_q = make_tmap_3d(p.qkv, 3LL * d, T, Bc, 3LL * d, (int64_t)T * 3 * d, 64, 128);
@@ -636,10 +651,10 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
   }
 
   // algorithmic FLOPs of one evaluation (GEMMs + attention), for roofline reporting
-  double f = p.g_t13.flops + p.g_t2.flops + p.g_tb.flops + p.g_y13.flops + p.g_y2.flops + p.g_in.flops +
+  double f = p.g_kvc_all.flops + p.g_t13.flops + p.g_t2.flops + p.g_tb.flops + p.g_y13.flops + p.g_y2.flops + p.g_in.flops +
              p.g_xe[0].flops + p.g_xe[1].flops + p.g_out.flops;
   for (auto& o : p.lay)
-    f += o.qkv.flops + o.wo.flops + o.q_c.flops + o.kv_c.flops + o.wo_c.flops + o.w13.flops + o.w2.flops +
+    f += o.qkv.flops + o.wo.flops + o.q_c.flops + o.wo_c.flops + o.w13.flops + o.w2.flops +
          4.0 * Bc * (double)T * T * d + 4.0 * Bc * (double)T * L * d;
   p.flops_per_eval = f;
   e->dit = std::move(P);
@@ -743,6 +758,7 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
     gemm(e, p.g_xe[b], st);
   }
   SAB_CUDA(cudaGetLastError());
+  gemm(e, p.g_kvc_all, st);
   for (int l = 0; l < NL; ++l) {
     const LayerW& W = e->layers[l];
     LayerOps& o = p.lay[l];
@@ -764,13 +780,12 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
       attention(e, a, Bc, H, st);
     }
     gemm(e, o.wo, st);
-    gemm(e, o.kv_c, st);
     gemm(e, o.q_c, st);
     if (!p.xa_fused) {
       AttnParams x{};
       x.q = p.qc; x.q_ld = d; x.q_col0 = 0;
-      x.k = p.kvc; x.k_ld = 2 * d; x.k_col0 = 0;
-      x.v = p.kvc; x.v_ld = 2 * d; x.v_col0 = d;
+      x.k = p.kvc; x.k_ld = 2LL * d * NL; x.k_col0 = l * 2 * d;
+      x.v = p.kvc; x.v_ld = 2LL * d * NL; x.v_col0 = l * 2 * d + d;
       x.o = p.att; x.o_ld = d; x.key_mask = p.text_mask; x.Tq = T; x.Tk = L; x.scale_log2 = sl2;
       attention(e, x, Bc, H, st);
     }

@@ -67,6 +67,8 @@ struct GemmParams {
   // qkv epilogue
   const float* qnorm_w; const float* knorm_w;  // [128]
   int n_q_end, n_k_end;                        // cols [0,n_q_end): q-norm, [n_q_end,n_k_end): k-norm, rest plain
+  int qkv_period, norm_w_stride;               // > 0: the column pattern repeats every qkv_period columns (several layers'
+                                               //      projections in one GEMM); repeat r uses norm weights + r*norm_w_stride
   const float2* rope; int rope_T; int use_rope; float eps;
   // fused cross-attention to a few text tokens (QKV mode, all heads are queries): instead of writing the normalised
   // queries, the epilogue attends to K/V [items*Tk, ld] (head-major columns; V at +xa_v_col0) and writes O
@@ -533,7 +535,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int hc = (BN >= 256 ? half * 128 : 0); hc < BN; hc += kHeadStep) {
           const int nh = n0 + hc;
           if (nh >= P.N) break;
-          const float* nw = (nh < P.n_q_end) ? P.qnorm_w : (nh < P.n_k_end ? P.knorm_w : nullptr);
+          const int rep = P.qkv_period > 0 ? nh / P.qkv_period : 0;
+          const int nhp = P.qkv_period > 0 ? nh - rep * P.qkv_period : nh;
+          const float* nw = (nhp < P.n_q_end) ? P.qnorm_w + rep * P.norm_w_stride
+                                               : (nhp < P.n_k_end ? P.knorm_w + rep * P.norm_w_stride : nullptr);
           if (P.xa_kv != nullptr) {
             // ---- fused cross-attention (thread == query row; scores are linear in the un-normalised query) ----
             const int t_thr = t_base + lane;                                   // row inside the GEMM item
