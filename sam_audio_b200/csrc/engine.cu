@@ -894,6 +894,10 @@ static CodecPlan* get_enc_plan(sab_engine* e, int items, long long S) {
   auto key = std::make_pair(items, S);
   auto it = e->enc_plans.find(key);
   if (it != e->enc_plans.end()) return it->second.get();
+  if (!e->enc_plans.empty()) {   // one resident plan per direction: a new clip length replaces the old workspace
+    SAB_CUDA(cudaDeviceSynchronize());
+    e->enc_plans.clear();
+  }
   const sab_config& c = e->cfg;
   auto CP = std::make_unique<CodecPlan>();
   CodecPlan& cp = *CP;
@@ -963,6 +967,10 @@ static CodecPlan* get_dec_plan(sab_engine* e, int items, long long T) {
   auto key = std::make_pair(items, T);
   auto it = e->dec_plans.find(key);
   if (it != e->dec_plans.end()) return it->second.get();
+  if (!e->dec_plans.empty()) {
+    SAB_CUDA(cudaDeviceSynchronize());
+    e->dec_plans.clear();
+  }
   const sab_config& c = e->cfg;
   auto CP = std::make_unique<CodecPlan>();
   CodecPlan& cp = *CP;
