@@ -388,7 +388,13 @@ def run_gpu(args):
                      "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
                      "share_of_step": g_ms / max(total_ms, 1e-9),
                      "profiled_ms_per_step": ms_prof / args.steps,
-                     "algorithmic_tflop_per_step": g_fl / 1e12 / args.steps},
+                     "algorithmic_tflop_per_step": g_fl / 1e12 / args.steps,
+                     "dominant_launch": (lambda t: {"tag": t, "launches": int(prof[t]["launches"]),
+                                                    "avg_launch_ms": prof[t]["ms"] / max(prof[t]["launches"], 1),
+                                                    "tflop_per_launch": prof[t]["flops"] / max(prof[t]["launches"], 1) / 1e12,
+                                                    "achieved": prof[t]["flops"] / max(prof[t]["ms"], 1e-9) / 1e9,
+                                                    "frac": prof[t]["flops"] / max(prof[t]["ms"], 1e-9) / 1e9 / peaks["tf_sustained"]})(
+                         max(gemm_tags, key=lambda t: prof[t]["ms"])) if gemm_tags else None},
         "breakdown_ms_per_step": {k: v / args.steps for k, v in groups.items()},
         "sdpa_tflops": att_tf,
         "kernels": {t: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] / args.steps,
