@@ -147,6 +147,11 @@ SAB_DEVICE float4 lds128(uint32_t addr) {
 
 // ----------------------------------------------------------------------------- math / packing
 SAB_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
+SAB_DEVICE float rcp_approx(float x) {   // one MUFU.RCP (<= 1 ulp), no IEEE-division slow path
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 SAB_DEVICE uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

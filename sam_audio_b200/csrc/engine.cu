@@ -1292,8 +1292,14 @@ static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_
         const int C0 = c.codec_encoder_dim;
         const long long n = cp.S * (C0 / 4);
         mark(e, st, "codec.enc.conv0", 2.0 * items * (double)cp.S * C0 * 7, (double)items * cp.S * (4.0 + C0 * 6.0));
-        enc_conv0_kernel<<<dim3((unsigned)((n + 255) / 256), items), 256, 0, st>>>(
-            wav_in, cp.S, C0, e->enc0_w, e->enc0_b, e->enc_blocks[0].ru[0].a0, cp.x_first, cp.a_first);
+        if (C0 % 4 == 0 && 256 % (C0 / 4) == 0) {
+          const long long per_block = (256 / (C0 / 4)) * ENC0_ITER;
+          enc_conv0_reg_kernel<<<dim3((unsigned)((cp.S + per_block - 1) / per_block), items), 256, 0, st>>>(
+              wav_in, cp.S, C0, e->enc0_w, e->enc0_b, e->enc_blocks[0].ru[0].a0, cp.x_first, cp.a_first);
+        } else {
+          enc_conv0_kernel<<<dim3((unsigned)((n + 255) / 256), items), 256, 0, st>>>(
+              wav_in, cp.S, C0, e->enc0_w, e->enc0_b, e->enc_blocks[0].ru[0].a0, cp.x_first, cp.a_first);
+        }
         break;
       }
       case CodecStep::LATENT_SPLIT: {
@@ -1306,8 +1312,13 @@ static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_
         const int C = c.codec_decoder_dim >> c.codec_n_rates;
         const int smem = ((DEC_LAST_TB + 6) * (C + 2) + 2) * 2 + 7 * C * 4;
         mark(e, st, "codec.dec.last", 2.0 * items * (double)cp.S * C * 7, (double)items * cp.S * (4.0 + C * 2.0));
-        dec_last_kernel<<<dim3((unsigned)((cp.S + DEC_LAST_TB - 1) / DEC_LAST_TB), items), DEC_LAST_TB, smem, st>>>(
-            cp.a_last, cp.S, C, e->dec_last_w, e->dec_last_b, out);
+        const dim3 rgrid((unsigned)((cp.S + 32 * DEC_SEG - 1) / (32 * DEC_SEG)), items);
+        if (C == 96) dec_last_reg_kernel<3><<<rgrid, 256, 0, st>>>(cp.a_last, cp.S, e->dec_last_w, e->dec_last_b, out);
+        else if (C == 64) dec_last_reg_kernel<2><<<rgrid, 256, 0, st>>>(cp.a_last, cp.S, e->dec_last_w, e->dec_last_b, out);
+        else if (C == 128) dec_last_reg_kernel<4><<<rgrid, 256, 0, st>>>(cp.a_last, cp.S, e->dec_last_w, e->dec_last_b, out);
+        else
+          dec_last_kernel<<<dim3((unsigned)((cp.S + DEC_LAST_TB - 1) / DEC_LAST_TB), items), DEC_LAST_TB, smem, st>>>(
+              cp.a_last, cp.S, C, e->dec_last_w, e->dec_last_b, out);
         break;
       }
       default: {

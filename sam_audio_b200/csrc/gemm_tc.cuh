@@ -404,10 +404,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.b2b_bias + c + j));
               const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.b2b_alpha + c + j));
               float x0 = v[j] + b4.x, x1 = v[j + 1] + b4.y, x2 = v[j + 2] + b4.z, x3 = v[j + 3] + b4.w, sn;
-              sn = __sinf(a4.x * x0); x0 = fmaf(sn * sn, 1.f / (a4.x + 1e-9f), x0);
-              sn = __sinf(a4.y * x1); x1 = fmaf(sn * sn, 1.f / (a4.y + 1e-9f), x1);
-              sn = __sinf(a4.z * x2); x2 = fmaf(sn * sn, 1.f / (a4.z + 1e-9f), x2);
-              sn = __sinf(a4.w * x3); x3 = fmaf(sn * sn, 1.f / (a4.w + 1e-9f), x3);
+              sn = __sinf(a4.x * x0); x0 = fmaf(sn * sn, rcp_approx(a4.x + 1e-9f), x0);
+              sn = __sinf(a4.y * x1); x1 = fmaf(sn * sn, rcp_approx(a4.y + 1e-9f), x1);
+              sn = __sinf(a4.z * x2); x2 = fmaf(sn * sn, rcp_approx(a4.z + 1e-9f), x2);
+              sn = __sinf(a4.w * x3); x3 = fmaf(sn * sn, rcp_approx(a4.w + 1e-9f), x3);
               pk[j >> 1] = pack_bf16(x0, x1);
               pk[(j >> 1) + 1] = pack_bf16(x2, x3);
             }
@@ -482,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (P.out_act) {   // Snake: v + sin^2(a v) / (a + 1e-9)
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.snake_alpha + (P.bias_mod ? (n % P.bias_mod) : n)));
-            const float4 i4 = make_float4(1.f / (a4.x + 1e-9f), 1.f / (a4.y + 1e-9f), 1.f / (a4.z + 1e-9f), 1.f / (a4.w + 1e-9f));
+            const float4 i4 = make_float4(rcp_approx(a4.x + 1e-9f), rcp_approx(a4.y + 1e-9f), rcp_approx(a4.z + 1e-9f), rcp_approx(a4.w + 1e-9f));
             __nv_bfloat16* o0 = P.out_act + row0 * P.out_act_ld + n;
             const long long st = 4 * P.out_act_ld;
 #pragma unroll
