@@ -147,6 +147,13 @@ SAB_DEVICE float4 lds128(uint32_t addr) {
 
 // ----------------------------------------------------------------------------- math / packing
 SAB_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// 16-byte global load that does not allocate in L1 (streamed once; plain ld.global, so in-place updates stay coherent)
+SAB_DEVICE float4 ldg_stream128(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 SAB_DEVICE float rcp_approx(float x) {   // one MUFU.RCP (<= 1 ulp), no IEEE-division slow path
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -109,7 +109,9 @@ SAB_DEVICE void cluster_sync_all() {
 SAB_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // default semantics (release at CTA scope): the accumulator hand-over is ordered by tcgen05.fence::before_thread_sync;
+  // a cluster-scope release would make every epilogue warp wait for its outstanding global stores (MEMBAR.GPU + ERRBAR)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: address of the leader CTA's barrier
 SAB_DEVICE void tma_load_2d_cg2(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
@@ -229,7 +231,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(smem_u32(tmem_slot)));
+  // consume the loaded value here: otherwise its first use sits inside the epilogue's chunk loop and every iteration
+  // waits on the load's scoreboard slot, which by then tracks the residual prefetches (ncu: 18% of the epilogue's time)
+  if (tmem_base == 0xFFFFFFFFu) __trap();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA) =====================
@@ -379,14 +385,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
             r4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (res0 && 4 * p < rl && n0 + c < P.N) r4[p] = *reinterpret_cast<const float4*>(res0 + p * res_step + c);
+            if (res0 && 4 * p < rl && n0 + c < P.N) r4[p] = ldg_stream128(res0 + p * res_step + c);
           }
         };
-        long long goff[8];                      // adaLN gate row of each pass (one integer division per tile, not per chunk)
+        int goff[8];                            // adaLN gate row of each pass (one integer division per tile, not per chunk)
         if (P.gate) {
 #pragma unroll
           for (int p = 0; p < 8; ++p)
-            goff[p] = (4 * p < rl) ? (long long)((int)(row0 + 4 * p) / P.gate_div) * P.gate_ld : 0;
+            goff[p] = (4 * p < rl) ? ((int)(row0 + 4 * p) / P.gate_div) * P.gate_ld : 0;
         }
         if constexpr (B2B) {
           // ---- first epilogue: Snake(acc0 + bias) -> bf16 -> the K-major swizzled A tile of the second GEMM ----
@@ -435,11 +441,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = half * 32; c < BN; c += 64) {
           if (n0 + c >= P.N) break;
           if (c + 64 < BN) load_res(c + 64, rr_n);
+          const int n = n0 + c + tr_c;
+          float4 g4[8];                         // gate values: requested before the TMEM read / transpose, used after
+          if (!B2B && P.gate) {                 // (the codec's back-to-back tiles have no gate: keep their registers)
+            const float* g0 = P.gate + n;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) g4[p] = __ldg(reinterpret_cast<const float4*>(g0 + goff[p]));
+          }
           float v[32];
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
           stage_put(v);
-          const int n = n0 + c + tr_c;
           float4 x[8];
           stage_get(x);
           if (P.bias) {
@@ -447,13 +459,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int p = 0; p < 8; ++p) { x[p].x += b4.x; x[p].y += b4.y; x[p].z += b4.z; x[p].w += b4.w; }
           }
-          if (P.gate) {
-            const float* g0 = P.gate + n;
+          if (!B2B && P.gate) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(g0 + goff[p]));
-              x[p].x *= g.x; x[p].y *= g.y; x[p].z *= g.z; x[p].w *= g.w;
-            }
+            for (int p = 0; p < 8; ++p) { x[p].x *= g4[p].x; x[p].y *= g4[p].y; x[p].z *= g4[p].z; x[p].w *= g4[p].w; }
           }
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
