@@ -146,7 +146,6 @@ SAB_DEVICE float4 lds128(uint32_t addr) {
 }
 
 // ----------------------------------------------------------------------------- math / packing
-SAB_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
 // 16-byte global load that does not allocate in L1 (streamed once; plain ld.global, so in-place updates stay coherent)
 SAB_DEVICE float4 ldg_stream128(const float* p) {
   float4 v;
@@ -159,6 +158,9 @@ SAB_DEVICE float rcp_approx(float x) {   // one MUFU.RCP (<= 1 ulp), no IEEE-div
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// x * sigmoid(x), branch-free (6 instructions; the IEEE division was ~20 with a slow-path branch per element and made up
+// about half of the instructions the ffn.w13 kernel issued); exp(-x) = inf gives rcp = +0 and the exact limit -0
+SAB_DEVICE float silu_f(float x) { return x * rcp_approx(1.f + __expf(-x)); }
 SAB_DEVICE uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

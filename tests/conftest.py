@@ -10,8 +10,30 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def usable_host_cores() -> int:
+    """Cores this process may actually use: the smaller of the affinity mask and the cgroup CPU quota.  GPU boxes
+    report 128 logical CPUs under a 16-core quota; torch's default (one thread per logical CPU) then oversubscribes
+    and the CPU oracle legs of the parity tests run several times slower, more so on a busy host."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for quota_file, period_file in (("/sys/fs/cgroup/cpu.max", None),
+                                    ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/sys/fs/cgroup/cpu/cpu.cfs_period_us")):
+        try:
+            if period_file is None:
+                q, per = open(quota_file).read().split()
+            else:
+                q, per = open(quota_file).read().strip(), open(period_file).read().strip()
+            if q not in ("max", "-1"):
+                n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    import torch
+    torch.set_num_threads(usable_host_cores())
 
 
 @pytest.fixture(scope="session")
