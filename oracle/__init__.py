@@ -22,8 +22,15 @@ Parity status
   PINNED — restate.py is checked against the reference's own modules run in
   this container (see tests/test_oracle_golden.py and make_golden.py).
 * DAC-VAE codec arithmetic (third-party ``dacvae @ main``, source absent from
-  /root/reference), T5 numerics (``transformers``), torchdiffeq: PARITY
-  UNPINNED by the reference — restated from the published Descript-DAC layout
-  and the reference's call sites (codec.py:45-89, config.py:10-41); the CUDA
-  path is checked against this restatement only.
+  /root/reference): PARITY UNPINNED by the reference.  The encoder / decoder
+  trunks are restated from the published Descript-DAC layout and the reference's
+  call sites (codec.py:45-89, config.py:10-41) and are pinned against an
+  independent implementation of that layout, ``transformers.models.dac``
+  (DacEncoder / DacDecoder, same weights, float64 agreement 1e-12:
+  tests/test_oracle_codec_vs_hf_dac.py).  Still unpinned: dacvae's bottleneck
+  convention beyond the reference's own call site (in_proj -> first half = mean,
+  codec.py:68) and anything dacvae adds on top of the Descript layout.
+* T5 numerics: the oracle IS ``transformers.T5EncoderModel`` (installed).
+  torchdiffeq (absent): fixed-grid midpoint restated, 32 evaluations at exact
+  multiples of 1/32 (model.py:22,285-290).
 """
