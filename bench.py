@@ -202,7 +202,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": n_warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": _config(args, 1, 1),
+        # the b200 arm's workload at this N (the driver pairs the two lines); the CPU leg times a bounded sample of it
+        # (one clip of the batch, see cpu_baseline.sample): clips/s does not depend on which clip
+        "config": _config(args, max(1, args.gpus), args.batch),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "cores_available": avail, "kind": "port",
                          "sample": SAMPLE_DESC, "detail_s": d},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
