@@ -90,7 +90,9 @@ class SAMAudio(torch.nn.Module):
             config = json.load(f)
         ctor_kwargs = {}
         for k, v in model_kwargs.items():
-            if k in config:
+            # reference base.py:49-51: keyword arguments override config keys; anything else (and ready-made
+            # modules such as text_encoder=...) goes to the constructor
+            if k in config and not isinstance(v, torch.nn.Module):
                 config[k] = v
             else:
                 ctor_kwargs[k] = v

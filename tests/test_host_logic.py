@@ -73,3 +73,32 @@ def test_shard_range_covers_everything_once():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_from_pretrained_local_directory_and_no_cpu_path(tmp_path):
+    """The reference's loading contract (base.py:17-62): a directory with config.json + checkpoint.pt; constructor
+    overrides are taken from config keys; encoder / ranker keys in the checkpoint are skipped (model.py:346-359);
+    weight-normed codec tensors are folded.  Without a GPU the model refuses to run instead of falling back."""
+    import json
+    from sam_audio_b200 import SAMAudio, SAMAudioProcessor
+    from sam_audio_b200.text_encoder import SyntheticTextEncoder
+    cfg = stand_in_config("sam-audio-tiny")
+    sd = make_state_dict(cfg, seed=0)
+    # store one codec conv in weight-norm form and add keys the reference ignores
+    w = sd.pop("audio_codec.encoder.block.0.weight")
+    sd["audio_codec.encoder.block.0.weight_v"] = 3.0 * w
+    sd["audio_codec.encoder.block.0.weight_g"] = w.flatten(1).norm(dim=1).view(-1, 1, 1)
+    sd["text_encoder.model.shared.weight"] = torch.zeros(4, 4)
+    sd["span_predictor.anything"] = torch.zeros(1)
+    (tmp_path / "config.json").write_text(json.dumps(cfg.to_dict()))
+    torch.save(sd, tmp_path / "checkpoint.pt")
+
+    m = SAMAudio.from_pretrained(str(tmp_path), text_encoder=SyntheticTextEncoder())
+    assert m.cfg.transformer.dim == cfg.transformer.dim and m.sample_rate == 48000
+    assert not any(k.startswith(("text_encoder.", "span_predictor.")) for k in m._state)
+    assert torch.allclose(m._state["audio_codec.encoder.block.0.weight"], w, atol=1e-6)
+    proc = SAMAudioProcessor.from_pretrained(str(tmp_path))
+    assert proc.audio_hop_length == 1920 and proc.audio_sampling_rate == 48000
+    batch = proc(descriptions=["thunder"], audios=[torch.zeros(1, 4000)])
+    with pytest.raises(RuntimeError, match="B200 only"):
+        m.eval().separate(batch)
