@@ -128,8 +128,19 @@ def main():
     nz = (b.anchor_alignment[0] == 2).nonzero().flatten()
     assert int(nz[0]) == 158 and int(nz[-1]) == 174
     pg["survey_example"] = dict(anchor_alignment=b.anchor_alignment, anchor_ids=b.anchor_ids)
+    # masked-video inputs as tensors (reference processor.py:131-155 tensor branch, :197-204): one frame per latent
+    # frame picked by linspace().round(), masked pixels zeroed
+    gv = torch.Generator().manual_seed(77)
+    vids = [torch.randint(0, 256, (n, 3, 4, 6), generator=gv, dtype=torch.uint8) for n in (30, 7, 1, 5)]
+    msks = [torch.randint(0, 2, (n, 1, 4, 6), generator=gv, dtype=torch.uint8) for n in (30, 7, 1, 5)]
+    masked = proc.mask_videos(vids, msks)
+    bv = proc(descriptions=desc, audios=auds, masked_videos=masked)
+    pg["video"] = dict(video_lens=[30, 7, 1, 5], masked=[m.clone() for m in masked],
+                       frames=[f.clone() for f in bv.masked_video])
     torch.save(pg, os.path.join(GOLDEN, "processor.pt"))
     print("processor: restatement bit-exact vs reference")
+    if "--processor-only" in sys.argv:
+        return
 
     # ---------------- DiT.forward + SAMAudio.forward (ragged, anchors) ----------------
     g = torch.Generator().manual_seed(7)
