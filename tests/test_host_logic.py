@@ -102,3 +102,22 @@ def test_from_pretrained_local_directory_and_no_cpu_path(tmp_path):
     batch = proc(descriptions=["thunder"], audios=[torch.zeros(1, 4000)])
     with pytest.raises(RuntimeError, match="B200 only"):
         m.eval().separate(batch)
+
+
+def test_t5_bucket_table_matches_transformers_and_hash_tokenizer_is_stable():
+    """Host side of the native T5 path: the relative-position bucket table handed to sab_t5_forward is transformers'
+    own bucketing (same fp32 expression, so boundaries round identically), for every length up to the 512-token cap."""
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from sam_audio_b200.text_encoder import _HashTokenizer, t5_relative_buckets
+    for L in (1, 2, 9, 40, 129, 512):
+        rp = torch.arange(L)[None, :] - torch.arange(L)[:, None]           # key - query
+        hf = T5Attention._relative_position_bucket(rp, bidirectional=True, num_buckets=32, max_distance=128)
+        tab = t5_relative_buckets(L)
+        assert tab.shape == (2 * L - 1,) and tab.dtype == torch.int32
+        assert torch.equal(tab[rp + L - 1].long(), hf)
+    tok = _HashTokenizer()
+    a = tok(["man speaking", "a dog barking loudly"])
+    b = tok(["man speaking", "a dog barking loudly"])
+    assert torch.equal(a["input_ids"], b["input_ids"]) and torch.equal(a["attention_mask"], b["attention_mask"])
+    assert a["input_ids"].shape == (2, 5) and a["input_ids"][0, 2] == 1 and a["input_ids"][0, 3] == 0   # </s>, then pad
+    assert a["attention_mask"].sum(1).tolist() == [3, 5]
