@@ -535,7 +535,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {  // EPI_QKV: each 128-col group is one head; this warp owns heads half, half+2, ... (BN=256: one each)
         int pos[8];                             // RoPE position of each pass (one modulo per tile)
 #pragma unroll
-        for (int p = 0; p < 8; ++p) pos[p] = (int)((row0 + 4 * p) % P.rope_T);
+        for (int p = 0; p < 8; ++p) pos[p] = (int)(((uint32_t)row0 + 4u * p) % (uint32_t)P.rope_T);   // rows < 2^31: no 64-bit division
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         constexpr int kHeadStep = (BN >= 256) ? 256 : 128;   // BN=128: both warps of a quarter share the single head
@@ -551,7 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ---- fused cross-attention (thread == query row; scores are linear in the un-normalised query) ----
             const int t_thr = t_base + lane;                                   // row inside the GEMM item
             const long long grow = (long long)item * P.rows_per_item + (t_thr < P.rows_per_item ? t_thr : P.rows_per_item - 1);
-            const int b = (int)(grow / P.xa_T);
+            const int b = (int)((uint32_t)grow / (uint32_t)P.xa_T);
             const __nv_bfloat16* kp = P.xa_kv + (long long)b * P.xa_Tk * P.xa_kv_ld + nh;
             const __nv_bfloat16* vp = kp + P.xa_v_col0;
             float ss = 0.f, sc[XA_MAX_TK];
