@@ -160,7 +160,8 @@ def cpu_sample(sd, cfg, n_threads: int, repeats: int = 1):
             return restate.samaudio_forward(sd, cfg, yy, feats, tf, t.expand(1), video, tm, ids, al, mask)
         dt = 1.0 / 16
         f0 = field(torch.tensor(0.0), y)
-        y = y + dt * field(torch.tensor(dt / 2), y + f0 * (dt / 2))
+        f1 = field(torch.tensor(dt / 2), y + f0 * (dt / 2))
+        y = y + dt * f1
         t2 = time.perf_counter()
         w = restate.codec_decode(sd, cc, y.transpose(1, 2).reshape(2, cc.codebook_dim, T))
         t3 = time.perf_counter()
@@ -169,7 +170,59 @@ def cpu_sample(sd, cfg, n_threads: int, repeats: int = 1):
         d["clip_s"] = d["encode_s"] + 16 * d["ode_step_s"] + d["decode_s"]
         if best is None or d["clip_s"] < best["clip_s"]:
             best = d
+        _CPU_SAMPLE_OUT.update(features=feats[:, :, : cc.codebook_dim], velocity=f1, latent=y, wav=w.view(2, -1))
     return 1.0 / best["clip_s"], best
+
+
+_CPU_SAMPLE_OUT = {}          # tensors of the last cpu_sample(): what the GPU parity gate is checked against
+
+
+def gpu_sample(model, cfg, dev):
+    """The SAME bounded sample as cpu_sample() (clip 0, prompt, noise; encode + one midpoint step of 1/16 + decode)
+    through the CUDA path — the parity gate of the bench line compares the two."""
+    from oracle import restate
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_noise, synthetic_text_features
+    cc = cfg.audio_codec
+    with torch.inference_mode():
+        feats = model._get_audio_features(synthetic_clip(0)[None].to(dev))
+        tf, tm = synthetic_text_features(["man speaking"])
+        T = feats.shape[1]
+        mask = torch.ones(1, T, dtype=torch.bool)
+        ids, al = restate.process_anchors(None, mask, cc.hop_length, cc.sample_rate)      # integer host logic
+        model._install_conditioning(feats, tf.to(dev), tm.to(dev), None, ids.to(dev), al.to(dev), mask.to(dev))
+        eng = model._ensure_engine()
+        y = synthetic_noise(1, T).to(dev)
+        dt = 1.0 / 16
+        f0, f1 = torch.empty_like(y), torch.empty_like(y)
+        eng.dit_forward(y, torch.zeros(1, device=dev), f0)
+        eng.dit_forward((y + f0 * (dt / 2)).contiguous(), torch.full((1,), dt / 2, device=dev), f1)
+        y1 = (y + dt * f1).contiguous()
+        w = torch.empty(1, 2, T * cc.hop_length, device=dev)
+        eng.decode(y1, 1, T, w)
+        torch.cuda.synchronize()
+    return dict(features=feats[:, :, : cc.codebook_dim].cpu(), velocity=f1.cpu(), latent=y1.cpu(), wav=w[0].cpu())
+
+
+PARITY_TOL = {"features_rel_l2": 2e-2, "velocity_rel_l2": 2e-2, "wav_snr_db": 30.0}
+
+
+def parity_gate(gpu, cpu):
+    import math
+
+    def rl2(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    r = {"features_rel_l2": rl2(gpu["features"], cpu["features"]),
+         "velocity_rel_l2": rl2(gpu["velocity"], cpu["velocity"]),
+         "latent_rel_l2": rl2(gpu["latent"], cpu["latent"]),
+         "wav_snr_db": -20.0 * math.log10(max(rl2(gpu["wav"], cpu["wav"]), 1e-30))}
+    r["rel_l2"], r["snr_db"] = r["velocity_rel_l2"], r["wav_snr_db"]
+    r["tolerance"] = PARITY_TOL
+    r["ok"] = bool(r["features_rel_l2"] <= PARITY_TOL["features_rel_l2"] and
+                   r["velocity_rel_l2"] <= PARITY_TOL["velocity_rel_l2"] and r["wav_snr_db"] >= PARITY_TOL["wav_snr_db"])
+    r["sample"] = ("clip 0 of the workload, same prompt and noise on both sides: DAC-VAE encode, one midpoint step of "
+                   "1/16 (2 DiT evaluations at the benchmarked model shape), DAC-VAE decode; CUDA path vs the fp32 "
+                   "CPU oracle (the cpu_baseline sample)")
+    return r
 
 
 SAMPLE_DESC = ("1 clip (10 s @ 48 kHz) through the oracle port on the host cores: DAC-VAE encode + 1 of the 16 "
@@ -218,11 +271,13 @@ def _config(args, world, batch):
     tc = stand_in_config(args.model).transformer
     return {
         "workload": f"{args.model} separate(): batch={batch}x10s@48kHz mono per GPU, text prompt, "
-                    f"reranking_candidates=1, predict_spans=False (PE-A-Frame span predictor is third-party and absent; "
+                    f"reranking_candidates={args.candidates} ({batch * args.candidates} ODE sequences per GPU; rankers "
+                    f"None = candidate 0, config.py:214-215), predict_spans=False (PE-A-Frame span predictor is "
+                    f"third-party and absent; "
                     f"at the pinned commit it does not change the audio), 16 midpoint steps = 32 DiT evaluations",
         "model_shape": f"stand-in (HF config.json is gated): dim={tc.dim} layers={tc.n_layers} heads={tc.n_heads} "
                        f"ffn={tc.ffn_hidden}; DAC-VAE 64/1024/1536 rates 2-8-10-12; random-init weights",
-        "global_batch": world * batch, "clip_seconds": 10, "sample_rate": 48000,
+        "global_batch": world * batch, "candidates": args.candidates, "clip_seconds": 10, "sample_rate": 48000,
         "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB)",
         "text_encoder": "t5-base shape, random init, hash tokenizer (no checkpoint on disk)",
     }
@@ -249,7 +304,10 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     cfg = stand_in_config(args.model)
-    B = args.batch
+    B, C = args.batch, args.candidates
+    if args.global_batch:                      # strong scaling: a fixed global batch split over the ranks
+        assert args.global_batch % world == 0, "--global-batch must be a multiple of the GPU count"
+        B = args.global_batch // world
     # ---- weights: generated on rank 0, ONE broadcast over NCCL/NVLink ----
     sd = make_state_dict(cfg, seed=0, device=dev) if rank == 0 else None
     if world > 1:
@@ -264,11 +322,13 @@ def run_gpu(args):
     del sd
     model._state = None
     torch.cuda.empty_cache()
+    # parity gate, GPU half (before the timed plan exists: a B=1 plan would otherwise evict the captured graph)
+    gpu_par = gpu_sample(model, cfg, dev) if sd_cpu is not None else None
 
     proc = SAMAudioProcessor(cfg.audio_codec.hop_length, cfg.audio_codec.sample_rate)
     clips = [synthetic_clip(rank * B + i).pin_memory() for i in range(B)]
     desc = synthetic_descriptions(B)
-    noise_host = synthetic_noise(B, 250, seed=4321 + rank).pin_memory()
+    noise_host = synthetic_noise(B * C, 250, seed=4321 + rank).pin_memory()
     h2d = sum(c.numel() * 4 for c in clips) + noise_host.numel() * 4
     out_host = torch.empty(B, 2, 480000, dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4
@@ -280,7 +340,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_resident(batch, noise):
-        out = model.separate(batch, noise=noise)
+        out = model.separate(batch, noise=noise, reranking_candidates=C)
         if world > 1:
             loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])
             return all_gather_waveforms(loc, [B] * world)
@@ -291,7 +351,7 @@ def run_gpu(args):
         if not batch.audios.is_pinned():
             batch.audios = batch.audios.pin_memory()
         batch = batch.to(dev)                                       # H2D
-        out = model.separate(batch, noise=noise_host.to(dev, non_blocking=True))
+        out = model.separate(batch, noise=noise_host.to(dev, non_blocking=True), reranking_candidates=C)
         loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])
         if world > 1:
             all_gather_waveforms(loc, [B] * world)
@@ -364,8 +424,17 @@ def run_gpu(args):
             groups["dit_gemm"] += v["ms"]
         else:
             groups["norm_elementwise"] += v["ms"]
+    # HBM-bound kernels: algorithmic bytes per launch / live launch time vs the measured copy bandwidth
+    hbm_tags = [t for t in prof if prof[t]["bytes"] > 0 and
+                t.startswith(("rmsnorm", "codec.", "gn_", "latent_split"))]
+    hbm = {t: {"launches_per_step": prof[t]["launches"] / args.steps,
+               "mb_per_launch": round(prof[t]["bytes"] / prof[t]["launches"] / 1e6, 2),
+               "ms_per_step": round(prof[t]["ms"] / args.steps, 3),
+               "gbs": round(prof[t]["bytes"] / max(prof[t]["ms"], 1e-9) / 1e6, 1),
+               "frac": round(prof[t]["bytes"] / max(prof[t]["ms"], 1e-9) / 1e6 / peaks["hbm"], 3)}
+           for t in sorted(hbm_tags, key=lambda t: -prof[t]["ms"])}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r1.json")
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r2.json")
     if os.path.exists(tpath):     # dram__bytes_read+write of the dominant launch (ffn.w13) from the committed ncu capture
         traffic = json.load(open(tpath))
     att = {t: v for t, v in prof.items() if t.startswith("sdpa")}
@@ -373,7 +442,7 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_val / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": _config(args, world, B),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -398,6 +467,8 @@ def run_gpu(args):
                                                     "frac": prof[t]["flops"] / max(prof[t]["ms"], 1e-9) / 1e9 / peaks["tf_sustained"]})(
                          max(gemm_tags, key=lambda t: prof[t]["ms"])) if gemm_tags else None},
         "breakdown_ms_per_step": {k: v / args.steps for k, v in groups.items()},
+        "hbm_kernels": {"peak_gbs": peaks["hbm"], "note": "algorithmic bytes (operands once + every epilogue stream "
+                        "once) / live launch time, sustained inside the step", "kernels": hbm},
         "sdpa_tflops": att_tf,
         "kernels": {t: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] / args.steps,
                         "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)}
@@ -409,6 +480,18 @@ def run_gpu(args):
         v, d = cpu_sample(sd_cpu, cfg, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "cores_available": avail, "kind": "port",
                                 "sample": SAMPLE_DESC, "detail_s": d}
+        # parity gate: no throughput is reported for a path whose results differ from the oracle's
+        line["parity"] = parity_gate(gpu_par, _CPU_SAMPLE_OUT)
+        if not line["parity"]["ok"]:
+            for k in ("value", "ms_per_step"):
+                line[k] = None
+            line["e2e"]["value"] = None
+            line["error"] = "parity gate failed: throughput withheld"
+            print(json.dumps(line), flush=True)
+            sys.exit(1)
+    else:
+        line["parity"] = {"checked": False, "why": "the CPU oracle leg runs on rank 0 at N=1 only (the same library and "
+                                                   "kernels run at every N); see tests/test_gpu_parity_large.py"}
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -423,6 +506,9 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="sam-audio-large")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--candidates", type=int, default=1, help="reranking_candidates (BASELINE config 4: 8)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: total clips split over the GPUs (overrides --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

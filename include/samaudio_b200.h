@@ -62,10 +62,12 @@ int sab_destroy(sab_engine* e);
  * `name` is the reference state-dict key (e.g. "transformer.layers.0.attention.wq.weight"; codec keys
  * "audio_codec.encoder.block.0.weight", weight-norm already folded).  `data` is fp32, contiguous, on host
  * (is_device=0) or device (is_device=1); it is consumed (repacked to bf16 / permuted) before returning.
- * Unknown names fail.  sab_finalize_weights() checks completeness and builds derived tables. */
+ * Unknown names fail.  sab_finalize_weights() checks completeness and builds derived tables; with
+ * allow_missing != 0 (load_state_dict(strict=False)) missing tensors keep their zero initialisation and their
+ * names are written, newline-separated, into missing_out (may be NULL). */
 int sab_load_weight(sab_engine* e, const char* name, const float* data, const int64_t* shape, int ndim,
                     int is_device, void* stream);
-int sab_finalize_weights(sab_engine* e, void* stream);
+int sab_finalize_weights(sab_engine* e, int allow_missing, char* missing_out, int64_t missing_cap, void* stream);
 
 /* Codec analysis.  replaces: DACVAE.forward (codec.py:65-78) + SAMAudio._get_audio_features (model.py:182-184).
  * wav [B, S] mono fp32 (S already padded to a multiple of hop by the caller = codec.py:72-78);
@@ -74,14 +76,20 @@ int sab_encode(sab_engine* e, const float* wav, int B, int64_t S, float* feature
 
 /* Conditioning, once per separate() call.  replaces the time-independent part of SAMAudio.forward:
  * align_inputs (model.py:108-128), AlignModalities (align.py:30-50), EmbedAnchors (model.py:54-65),
- * memory_proj (model.py:92,172).
- *  features       [Bc, T, 256]      (sab_encode output, already repeated per candidate)
- *  text_features  [Bc, L, text_dim] ; text_mask [Bc, L] uint8 (1 = token)
- *  video_features [Bc, vision_dim, T] or NULL (= zeros, model.py:188-189)
- *  anchor_ids [Bc, n_ids] int64 ; anchor_alignment [Bc, T] int64 ; audio_pad_mask [Bc, T] uint8 (1 = frame) */
-int sab_prepare(sab_engine* e, int Bc, int T, int L, const float* features, const float* text_features,
+ * memory_proj (model.py:92,172), and _repeat_for_reranking (model.py:193-203): every input is per CLIP
+ * and the `candidates` sequences of a clip (candidate-minor, sequence = clip * candidates + k) share it
+ * without being materialised; the ODE state has B * candidates sequences.
+ *  features       [B, T, 256]      (sab_encode output)
+ *  text_features  [B, L, text_dim] ; text_mask [B, L] uint8 (1 = token)
+ *  video_features [B, vision_dim, T] or NULL (= zeros, model.py:188-189)
+ *  anchor_ids [B, n_ids] int64 ; anchor_alignment [B, T] int64 ; audio_pad_mask [B, T] uint8 (1 = frame)
+ *  flags: SAB_PREP_* — the three `None` cases of SAMAudio.forward (separate() never passes None). */
+#define SAB_PREP_NO_VIDEO_TERM 1 /* masked_video_features=None: AlignModalities returns its input (align.py:41-42) */
+#define SAB_PREP_NO_ANCHORS 2    /* anchor_ids=None: EmbedAnchors returns its input (model.py:57-58); ids may be NULL */
+#define SAB_PREP_NO_TEXT 4       /* text_features=None: memory = time embedding only (model.py:170-172); L must be 1 */
+int sab_prepare(sab_engine* e, int B, int candidates, int T, int L, const float* features, const float* text_features,
                 const uint8_t* text_mask, const float* video_features, const int64_t* anchor_ids, int n_ids,
-                const int64_t* anchor_alignment, const uint8_t* audio_pad_mask, void* stream);
+                const int64_t* anchor_alignment, const uint8_t* audio_pad_mask, int flags, void* stream);
 
 /* One ODE function evaluation.  replaces: SAMAudio.forward / DiT.forward (model.py:130-180,
  * transformer.py:473-524) on the conditioning installed by sab_prepare.

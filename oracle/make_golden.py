@@ -175,6 +175,17 @@ def main():
         print(f"SAMAudio.forward[{tag}] restatement vs reference: rel_l2={e:.3e}")
         assert e < 2e-5, e
         outs[tag] = r
+    # the three `None` cases of SAMAudio.forward (no video term / no anchor term / time-only memory)
+    for tag, kw in (("none_video_anchors", dict(text_features=text, text_mask=mem_mask)),
+                    ("none_text", dict(text_features=None, text_mask=None))):
+        r = model.forward(noisy, feats, kw["text_features"], time, masked_video_features=None,
+                          text_mask=kw["text_mask"], anchor_ids=None, anchor_alignment=None, audio_pad_mask=pad_mask)
+        o = restate.samaudio_forward(sd, cfg, noisy, feats, kw["text_features"], time, None, kw["text_mask"], None, None,
+                                     pad_mask)
+        e = rel_l2(o, r)
+        print(f"SAMAudio.forward[{tag}] restatement vs reference: rel_l2={e:.3e}")
+        assert e < 2e-5, e
+        outs[tag] = r
     torch.save(dict(noisy=noisy, feats=feats, text=text, video=video, time=time, text_mask=mem_mask,
                     anchor_ids=ids, anchor_alignment=al, pad_mask=pad_mask, out=outs),
                os.path.join(GOLDEN, "samaudio_forward_tiny.pt"))
@@ -184,7 +195,7 @@ def main():
     auds2 = [synthetic.synthetic_clip(i, n) for i, n in enumerate(lens2)]
     desc2 = synthetic.synthetic_descriptions(2)
     sep = {}
-    for cand in (1, 2):
+    for cand in (1, 2, 8):
         batch = proc(descriptions=desc2, audios=auds2)
         Tn = int(batch.sizes.max())
         noise = synthetic.synthetic_noise(2 * cand, Tn)

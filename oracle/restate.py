@@ -202,12 +202,14 @@ def conditioning(sd: SD, audio_features, video_features, anchor_ids, anchor_alig
     W, b = sd["proj.weight"], sd["proj.bias"]
     c2 = audio_features.shape[-1]
     x = F.linear(audio_features, W[:, 2 * c2:3 * c2], b)      # middle third multiplies zeros
-    pc = F.conv1d(video_features, sd["align_masked_video.conv.weight"], sd["align_masked_video.conv.bias"])
-    pc = F.layer_norm(pc.permute(0, 2, 1), (W.shape[0],), sd["align_masked_video.layer_norm.weight"],
-                      sd["align_masked_video.layer_norm.bias"], eps=1e-5)
-    x = x + torch.tanh(sd["align_masked_video.gate"]) * pc
-    emb = sd["embed_anchors.embed.weight"][anchor_ids.gather(1, anchor_alignment)]
-    x = x + torch.tanh(sd["embed_anchors.gate"]) * F.linear(emb, sd["embed_anchors.proj.weight"])
+    if video_features is not None:                             # align.py:41-42: None -> input unchanged
+        pc = F.conv1d(video_features, sd["align_masked_video.conv.weight"], sd["align_masked_video.conv.bias"])
+        pc = F.layer_norm(pc.permute(0, 2, 1), (W.shape[0],), sd["align_masked_video.layer_norm.weight"],
+                          sd["align_masked_video.layer_norm.bias"], eps=1e-5)
+        x = x + torch.tanh(sd["align_masked_video.gate"]) * pc
+    if anchor_ids is not None:                                 # model.py:57-58: None -> input unchanged
+        emb = sd["embed_anchors.embed.weight"][anchor_ids.gather(1, anchor_alignment)]
+        x = x + torch.tanh(sd["embed_anchors.gate"]) * F.linear(emb, sd["embed_anchors.proj.weight"])
     return x
 
 
@@ -218,7 +220,9 @@ def samaudio_forward(sd: SD, cfg, noisy_audio, audio_features, text_features, ti
     x = F.linear(noisy_audio, sd["proj.weight"][:, :c2]) + conditioning(
         sd, audio_features, masked_video_features, anchor_ids, anchor_alignment)
     temb = sinusoidal_embedding(time, cfg.transformer.dim)[:, None]
-    memory = F.linear(text_features, sd["memory_proj.weight"], sd["memory_proj.bias"]) + temb
+    memory = temb                                              # model.py:170-172: text None -> time-only memory
+    if text_features is not None:
+        memory = F.linear(text_features, sd["memory_proj.weight"], sd["memory_proj.bias"]) + temb
     return dit_forward(sd, cfg.transformer, x, time, audio_pad_mask, memory, text_mask)
 
 

@@ -62,9 +62,9 @@ def lib() -> ctypes.CDLL:
         L.sab_create.argtypes = [ctypes.POINTER(SabConfig), i32, ctypes.POINTER(vp)]
         L.sab_destroy.argtypes = [vp]
         L.sab_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, i32, vp]
-        L.sab_finalize_weights.argtypes = [vp, vp]
+        L.sab_finalize_weights.argtypes = [vp, i32, ctypes.c_char_p, i64, vp]
         L.sab_encode.argtypes = [vp, vp, i32, i64, vp, vp]
-        L.sab_prepare.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp]
+        L.sab_prepare.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]
         L.sab_dit_forward.argtypes = [vp, vp, vp, vp, vp]
         L.sab_solve.argtypes = [vp, vp, i32, vp, vp]
         L.sab_decode.argtypes = [vp, vp, i32, i32, vp, vp]
@@ -86,6 +86,9 @@ def lib() -> ctypes.CDLL:
         L.sab_t5_launch_count.restype = i64
         _lib = L
     return _lib
+
+
+PREP_NO_VIDEO_TERM, PREP_NO_ANCHORS, PREP_NO_TEXT = 1, 2, 4   # include/samaudio_b200.h SAB_PREP_*
 
 
 def check(rc: int) -> None:
@@ -149,17 +152,22 @@ class Engine:
         check(lib().sab_load_weight(self._h, name.encode(), t.data_ptr(), shape, max(t.dim(), 1),
                                     1 if t.is_cuda else 0, stream_ptr()))
 
-    def finalize(self):
-        check(lib().sab_finalize_weights(self._h, stream_ptr()))
+    def finalize(self, allow_missing: bool = False):
+        """Returns the list of missing keys (empty unless allow_missing)."""
+        import ctypes as C
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().sab_finalize_weights(self._h, 1 if allow_missing else 0, buf, len(buf), stream_ptr()))
+        return [k for k in buf.value.decode().split("\n") if k]
 
     def encode(self, wav: torch.Tensor, features: torch.Tensor):
         B, S = wav.shape
         check(lib().sab_encode(self._h, wav.data_ptr(), B, S, features.data_ptr(), stream_ptr()))
 
-    def prepare(self, Bc, T, L, features, text, text_mask, video, anchor_ids, anchor_alignment, pad_mask):
-        check(lib().sab_prepare(self._h, Bc, T, L, features.data_ptr(), text.data_ptr(), text_mask.data_ptr(),
-                                ptr(video), anchor_ids.data_ptr(), anchor_ids.shape[1],
-                                anchor_alignment.data_ptr(), pad_mask.data_ptr(), stream_ptr()))
+    def prepare(self, B, candidates, T, L, features, text, text_mask, video, anchor_ids, anchor_alignment, pad_mask,
+                flags=0):
+        check(lib().sab_prepare(self._h, B, candidates, T, L, features.data_ptr(), ptr(text), text_mask.data_ptr(),
+                                ptr(video), ptr(anchor_ids), 0 if anchor_ids is None else anchor_ids.shape[1],
+                                ptr(anchor_alignment), pad_mask.data_ptr(), flags, stream_ptr()))
 
     def dit_forward(self, noisy, time, out):
         check(lib().sab_dit_forward(self._h, noisy.data_ptr(), time.data_ptr(), out.data_ptr(), stream_ptr()))

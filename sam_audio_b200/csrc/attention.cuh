@@ -19,7 +19,12 @@ struct AttnParams {
   const uint8_t* key_mask;                              // [items, Tk] (1 = attend) or null
   int Tq, Tk;
   float scale_log2;                                     // (1/sqrt(128)) * log2(e)
+  int kv_div, mask_div;                                 // K/V item = query item / kv_div, mask row = query item / mask_div
+                                                        // (the candidates of one clip share the clip's text K/V and its
+                                                        // masks); 0 or 1: same item
 };
+SAB_DEVICE int attn_kv_item(const AttnParams& P, int item) { return P.kv_div > 1 ? item / P.kv_div : item; }
+SAB_DEVICE int attn_mask_item(const AttnParams& P, int item) { return P.mask_div > 1 ? item / P.mask_div : item; }
 
 constexpr int ATT_BQ = 64, ATT_BK = 64, ATT_D = 128, ATT_THREADS = 128;
 constexpr int ATT_TILE_BYTES = 64 * ATT_D * 2;  // 16 KB
@@ -75,9 +80,10 @@ attention_kernel(const AttnParams P) {
   const int q0 = qt * ATT_BQ;
 
   const __nv_bfloat16* qb = P.q + (long long)item * P.Tq * P.q_ld + P.q_col0 + head * ATT_D;
-  const __nv_bfloat16* kb = P.k + (long long)item * P.Tk * P.k_ld + P.k_col0 + head * ATT_D;
-  const __nv_bfloat16* vb = P.v + (long long)item * P.Tk * P.v_ld + P.v_col0 + head * ATT_D;
-  const uint8_t* mask = P.key_mask ? P.key_mask + (long long)item * P.Tk : nullptr;
+  const int kv_item = attn_kv_item(P, item);
+  const __nv_bfloat16* kb = P.k + (long long)kv_item * P.Tk * P.k_ld + P.k_col0 + head * ATT_D;
+  const __nv_bfloat16* vb = P.v + (long long)kv_item * P.Tk * P.v_ld + P.v_col0 + head * ATT_D;
+  const uint8_t* mask = P.key_mask ? P.key_mask + (long long)attn_mask_item(P, item) * P.Tk : nullptr;
   const int n_kt = (P.Tk + ATT_BK - 1) / ATT_BK;
 
   load_tile(sQ, qb, P.q_ld, q0, P.Tq, tid);
@@ -229,8 +235,9 @@ xattn_small_kernel(const AttnParams P) {
   __shared__ float sBias[TK];
   const int qt = blockIdx.x, head = blockIdx.y, item = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat16* kb = P.k + (long long)item * P.Tk * P.k_ld + P.k_col0 + head * ATT_D;
-  const __nv_bfloat16* vb = P.v + (long long)item * P.Tk * P.v_ld + P.v_col0 + head * ATT_D;
+  const int kv_item = attn_kv_item(P, item);
+  const __nv_bfloat16* kb = P.k + (long long)kv_item * P.Tk * P.k_ld + P.k_col0 + head * ATT_D;
+  const __nv_bfloat16* vb = P.v + (long long)kv_item * P.Tk * P.v_ld + P.v_col0 + head * ATT_D;
   for (int i = tid; i < TK * (ATT_D / 8); i += XATT_THREADS) {   // 8 dims per thread, converted to fp32 once
     const int j = i / (ATT_D / 8), c = (i % (ATT_D / 8)) * 8;
     uint4 kr = make_uint4(0u, 0u, 0u, 0u), vr = kr;
@@ -250,7 +257,7 @@ xattn_small_kernel(const AttnParams P) {
     *reinterpret_cast<float4*>(&sV[j][((i0 + 1) * 8 + l8) * 4]) = make_float4(vf[4], vf[5], vf[6], vf[7]);
   }
   if (tid < TK)
-    sBias[tid] = (tid < P.Tk && (!P.key_mask || P.key_mask[(long long)item * P.Tk + tid])) ? 0.f : -INFINITY;
+    sBias[tid] = (tid < P.Tk && (!P.key_mask || P.key_mask[(long long)attn_mask_item(P, item) * P.Tk + tid])) ? 0.f : -INFINITY;
   // this lane: row (pass*32 + warp*4 + lane/8), dims [16*(lane%8), +16)
   const int sub = lane >> 3, d0 = (lane & 7) * 16;
   const __nv_bfloat16* qb = P.q + (long long)item * P.Tq * P.q_ld + P.q_col0 + head * ATT_D + d0;

@@ -29,6 +29,7 @@ struct AttnTcParams {
   __nv_bfloat16* o; long long o_ld;
   const uint8_t* key_mask;          // [items, Tk] or null
   int Tq, Tk, heads, items;
+  int mask_div;                     // mask row = item / mask_div (candidates share their clip's pad mask); 0/1: item
   int q_col0, k_col0, v_col0;       // column of head 0 inside the fused QKV row
   float scale_log2;
   // debug knobs for bring-up of the MN-major V descriptor (bytes)
@@ -194,7 +195,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q /*box 64 x 128*/,
       // key validity bits of this item (sequence end + padding mask), one ballot per 32 keys
       uint32_t kbits[8];
       {
-        const uint8_t* mk = P.key_mask ? P.key_mask + (long long)item * P.Tk : nullptr;
+        const uint8_t* mk = P.key_mask ? P.key_mask + (long long)(P.mask_div > 1 ? item / P.mask_div : item) * P.Tk : nullptr;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int key = c * 32 + lane;

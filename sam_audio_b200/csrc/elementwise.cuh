@@ -11,23 +11,25 @@ namespace sab {
 // one warp per row.
 // ---------------------------------------------------------------------------------------------
 template <int kVecPerLane>  // d = kVecPerLane * 128
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (kVecPerLane > 24) ? 1 : 2)
 rmsnorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_ld, int rows_per_item,
                    __nv_bfloat16* __restrict__ out, int M, float eps) {
-  // Two streaming passes per row (the second one hits L1/L2): keeps the register count low enough for full
-  // occupancy, which is what hides HBM latency here (the single-pass, row-in-registers version ran at 8 warps/SM).
+  // Single pass: the row lives in registers (kVecPerLane float4 per lane, 88 floats at d = 2816), so x is read from
+  // HBM exactly once (6 B per element: 4 read + 2 written).  All of a lane's loads are issued back to back
+  // (streaming, no L1 allocation) before the reduction; 2 CTAs x 8 warps per SM keep >100 KB of loads in flight,
+  // several times the bandwidth-latency product.  The two-pass version re-read every row (10 B per element).
   constexpr int d = kVecPerLane * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
+  const float* xr = x + (long long)row * d + lane * 4;
+  float4 v[kVecPerLane];
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) v[i] = ldg_stream128(xr + i * 128);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
-    const float4 v = xr[lane + i * 32];
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
+  for (int i = 0; i < kVecPerLane; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   ss = warp_sum(ss);
   const float rstd = rsqrtf(ss / (float)d + eps);
   const long long b = row / rows_per_item;
@@ -35,15 +37,14 @@ rmsnorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_ld);
   const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_ld);
   uint2* orow = reinterpret_cast<uint2*>(out + (long long)row * d);
-#pragma unroll 2
+#pragma unroll
   for (int i = 0; i < kVecPerLane; ++i) {
     const int c = lane + i * 32;
-    const float4 v = xr[c];
     const float4 ww = __ldg(wr + c), s1 = __ldg(sc + c), s0 = __ldg(sh + c);
-    const float a = v.x * rstd * ww.x * (1.f + s1.x) + s0.x;
-    const float bb = v.y * rstd * ww.y * (1.f + s1.y) + s0.y;
-    const float cc = v.z * rstd * ww.z * (1.f + s1.z) + s0.z;
-    const float dd = v.w * rstd * ww.w * (1.f + s1.w) + s0.w;
+    const float a = v[i].x * rstd * ww.x * (1.f + s1.x) + s0.x;
+    const float bb = v[i].y * rstd * ww.y * (1.f + s1.y) + s0.y;
+    const float cc = v[i].z * rstd * ww.z * (1.f + s1.z) + s0.z;
+    const float dd = v[i].w * rstd * ww.w * (1.f + s1.w) + s0.w;
     orow[c] = make_uint2(pack_bf16(a, bb), pack_bf16(cc, dd));
   }
 }
@@ -85,11 +86,12 @@ __global__ void build_mod_kernel(const float* __restrict__ tables /*[L,6,d]*/, c
 // Timestep features (transformer.py:236-253: cat(cos,sin) of t*exp(-ln(1e4) i/128), raw t)  -> bf16 [B,256]
 // and the memory input (model.py:30-42,170-172: memory_proj(text) + cat(cos,sin)(t*exp(-ln(1e4) i/(d/2)))) -> bf16 [B*L,d]
 // ---------------------------------------------------------------------------------------------
-__global__ void time_features_kernel(const float* __restrict__ time /*[B]*/, int B, int d, int L,
+__global__ void time_features_kernel(const float* __restrict__ time /*[B*cand]*/, int B /*sequences*/, int cand, int d, int L,
                                      __nv_bfloat16* __restrict__ tfreq /*[B,256]*/,
-                                     const float* __restrict__ mem_base /*[B*L,d]*/,
-                                     __nv_bfloat16* __restrict__ mem_in /*[B*L,d]*/) {
-  const long long n1 = (long long)B * 256, n2 = (long long)B * L * d;
+                                     const float* __restrict__ mem_base /*[B/cand*L,d]*/,
+                                     __nv_bfloat16* __restrict__ mem_in /*[B/cand*L,d]*/) {
+  // the text memory is per clip: its time is that of the clip's first candidate (all equal inside a solve)
+  const long long n1 = (long long)B * 256, n2 = (long long)(B / cand) * L * d;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n1 + n2;
        i += (long long)gridDim.x * blockDim.x) {
     if (i < n1) {
@@ -105,7 +107,7 @@ __global__ void time_features_kernel(const float* __restrict__ time /*[B]*/, int
       const int half = d / 2;
       const int k = c < half ? c : c - half;
       const float f = expf(-logf(10000.f) * (float)k / (float)half);
-      const float a = time[b] * f;
+      const float a = time[(long long)b * cand] * f;
       mem_in[e] = __float2bfloat16(mem_base[e] + (c < half ? cosf(a) : sinf(a)));
     }
   }
@@ -194,25 +196,32 @@ gn_silu_kernel(const float* __restrict__ x, const double* __restrict__ partial, 
 // one warp per row.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-cond_finish_kernel(float* __restrict__ cond, int M, int d, int T,
-                   const float* __restrict__ vproj /*[M,d] or null*/, const float* __restrict__ ln_w,
+cond_finish_kernel(float* cond /*[M,d] per sequence*/, const float* cond_clip /*[M/cand,d]; == cond when cand == 1*/,
+                   int M, int d, int T, int cand,
+                   const float* __restrict__ vproj /*[M/cand,d] or null*/, const float* __restrict__ ln_w,
                    const float* __restrict__ ln_b, const float* __restrict__ vconst /*[d] (used when vproj null)*/,
                    const float* __restrict__ gate_v, const float* __restrict__ anchor_table /*[n_anchor+1, d]*/,
                    const long long* __restrict__ anchor_ids, int n_ids, const long long* __restrict__ anchor_align,
-                   const float* __restrict__ gate_a) {
+                   const float* __restrict__ gate_a, int video_term, int anchor_term) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const int b = row / T, t = row % T;
-  const float gv = tanhf(gate_v[0]), ga = tanhf(gate_a[0]);
-  const long long slot = anchor_align[(long long)b * T + t];
-  const long long id = anchor_ids[(long long)b * n_ids + slot];
-  const float* er = anchor_table + id * d;
+  const int b = (row / T) / cand, t = row % T;       // clip of this sequence row
+  const long long crow = (long long)b * T + t;
+  // forward(masked_video_features=None) / forward(anchor_ids=None) leave the input unchanged (align.py:41-42,
+  // model.py:57-58); separate() always supplies both (zeros video = the constant term, <null> anchors)
+  const float gv = video_term ? tanhf(gate_v[0]) : 0.f, ga = anchor_term ? tanhf(gate_a[0]) : 0.f;
+  const float* er = anchor_table;
+  if (anchor_term) {
+    const long long slot = anchor_align[crow];
+    er = anchor_table + anchor_ids[(long long)b * n_ids + slot] * d;
+  }
   float* cr = cond + (long long)row * d;
+  const float* ci = cond_clip + crow * d;
   float mean = 0.f, rstd = 0.f;
   const float* vr = nullptr;
-  if (vproj) {
-    vr = vproj + (long long)row * d;
+  if (vproj && video_term) {
+    vr = vproj + crow * d;
     float s = 0.f;
     for (int c = lane; c < d; c += 32) s += vr[c];
     mean = warp_sum(s) / (float)d;
@@ -221,8 +230,8 @@ cond_finish_kernel(float* __restrict__ cond, int M, int d, int T,
     rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
   }
   for (int c = lane; c < d; c += 32) {
-    const float vterm = vproj ? ((vr[c] - mean) * rstd * ln_w[c] + ln_b[c]) : vconst[c];
-    cr[c] += gv * vterm + ga * er[c];
+    const float vterm = vr ? ((vr[c] - mean) * rstd * ln_w[c] + ln_b[c]) : vconst[c];
+    cr[c] = ci[c] + gv * vterm + ga * er[c];
   }
 }
 

@@ -22,20 +22,54 @@ using namespace sab;
 typedef __nv_bfloat16 bf16;
 
 static thread_local std::string g_last_error;
-static int g_sm_count = 0;
+
+// ---- per-device state (several engines on different GPUs may live in one process) ----
+constexpr int kMaxDevices = 64;
+static int cur_device() {
+  int d = 0;
+  SAB_CUDA(cudaGetDevice(&d));
+  SAB_CHECK(d >= 0 && d < kMaxDevices, "device index %d out of range", d);
+  return d;
+}
+static int sm_count() {   // of the current device
+  static int cached[kMaxDevices] = {0};
+  const int d = cur_device();
+  if (!cached[d]) {
+    cudaDeviceProp prop;
+    SAB_CUDA(cudaGetDeviceProperties(&prop, d));
+    cached[d] = prop.multiProcessorCount;
+  }
+  return cached[d];
+}
+// cudaFuncSetAttribute is per device: once per (kernel instantiation, device)
+template <typename K>
+static void ensure_dynamic_smem(K kern, int smem) {
+  static bool configured[kMaxDevices] = {false};
+  const int d = cur_device();
+  if (!configured[d]) {
+    SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[d] = true;
+  }
+}
+// every entry point runs on its engine's device whatever the caller's current device is, and restores it
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    int cur = 0;
+    SAB_CUDA(cudaGetDevice(&cur));
+    if (cur != dev) { SAB_CUDA(cudaSetDevice(dev)); prev = cur; }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // =====================================================================================================
 // GEMM dispatch
 // =====================================================================================================
 template <int BN, int BK, int MODE, int CG, bool B2B = false>
 static void launch_gemm_inst(const GemmOp& op, cudaStream_t st) {
-  static bool configured = false;
   auto kern = gemm_tc_kernel<BN, BK, MODE, CG, B2B>;
   constexpr int smem = GemmSmem<BN, BK, CG, B2B>::kTotal;
-  if (!configured) {
-    SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  ensure_dynamic_smem(kern, smem);
   if (CG == 1) {
     kern<<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, op.b2b ? op.tmW : op.tmB, op.P);
   } else {
@@ -152,8 +186,10 @@ static GemmOp make_gemm(const char* tag, const AView& A, const bf16* B, int N, i
   P.gate_div = 1;
   P.eps = 1e-5f;
   const long long tiles = (long long)P.n_items * P.tiles_per_item * P.n_tiles_n;
-  op.grid = (int)std::min<long long>(tiles, g_sm_count / cg) * cg;
+  op.grid = (int)std::min<long long>(tiles, sm_count() / cg) * cg;
   op.flops = 2.0 * (double)A.rows * (double)A.items * (double)N * (double)ktot;
+  op.rows = (double)A.rows * (double)A.items;
+  op.in_bytes = op.rows * (double)A.cols * 2.0 + (double)N * (double)ktot * 2.0;
   SAB_CHECK(N % 32 == 0, "%s: N=%d must be a multiple of 32", tag, N);
   return op;
 }
@@ -510,8 +546,10 @@ struct LayerOps {
   GemmOp qkv, wo, q_c, kv_c, wo_c, w13, w2;
 };
 struct DitPlan {
+  int B = 0, cand = 1;                  // clips and candidates per clip: Bc = B * cand sequences (candidate-minor)
   int Bc = 0, T = 0, L = 0;
-  int64_t M = 0, ML = 0;
+  int64_t M = 0, MB = 0, ML = 0;        // sequence rows Bc*T, clip rows B*T, clip text rows B*L
+  float* condB = nullptr;               // clip-level conditioning GEMM output (aliases cond when cand == 1)
   DevicePool pool;
   // activations
   float *y, *ymid, *cond, *x0, *c1, *h, *t, *t0, *mod, *fin, *mem_base, *time_dev, *vproj;
@@ -538,19 +576,25 @@ struct DitPlan {
   ~DitPlan() { if (solve_graph) cudaGraphExecDestroy(solve_graph); }
 };
 
-static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
+// Conditioning (features, text, video, anchors, masks) is per CLIP; the candidates of a clip (model.py:193-203) share it:
+// the once-per-call GEMMs and the text path (memory, y_embedder, cross K/V) run on B clips and the per-sequence
+// consumers index clip = sequence / cand.  Inside sab_solve every sequence sees the same time, so the text path of
+// a clip is the same for all of its candidates; sab_dit_forward is only used with cand == 1.
+static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
+  const int Bc = B * cand;
   const sab_config& c = e->cfg;
   const int d = c.dim, hid = c.ffn_hidden, NL = c.n_layers;
   auto P = std::make_unique<DitPlan>();
   DitPlan& p = *P;
-  p.Bc = Bc; p.T = T; p.L = L;
-  const int64_t M = (int64_t)Bc * T, ML = (int64_t)Bc * L;
-  p.M = M; p.ML = ML;
+  p.B = B; p.cand = cand; p.Bc = Bc; p.T = T; p.L = L;
+  const int64_t M = (int64_t)Bc * T, MB = (int64_t)B * T, ML = (int64_t)B * L;
+  p.M = M; p.MB = MB; p.ML = ML;
   SAB_CHECK(T <= e->rope_len, "T=%d exceeds the RoPE table (%d)", T, e->rope_len);
   DevicePool& w = p.pool;
   p.y = w.alloc<float>(M * 256); p.ymid = w.alloc<float>(M * 256);
   p.cond = w.alloc<float>(M * d); p.x0 = w.alloc<float>(M * d); p.c1 = w.alloc<float>(M * d);
-  p.h = w.alloc<float>(M * d); p.vproj = w.alloc<float>(M * d);
+  p.h = w.alloc<float>(M * d); p.vproj = w.alloc<float>(MB * d);
+  p.condB = cand == 1 ? p.cond : w.alloc<float>(MB * d);
   p.t = w.alloc<float>((int64_t)Bc * d); p.t0 = w.alloc<float>((int64_t)Bc * 6 * d);
   p.mod = w.alloc<float>((int64_t)NL * Bc * 6 * d); p.fin = w.alloc<float>((int64_t)Bc * 2 * d);
   p.mem_base = w.alloc<float>(ML * d);
@@ -561,19 +605,19 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
   p.tfreq = w.alloc<bf16>((int64_t)Bc * 256); p.t_h = w.alloc<bf16>((int64_t)Bc * d);
   p.t_silu = w.alloc<bf16>((int64_t)Bc * d);
   p.mem_in = w.alloc<bf16>(ML * d); p.y_h = w.alloc<bf16>(ML * d); p.ymem = w.alloc<bf16>(ML * d);
-  p.feat_bf = w.alloc<bf16>(M * 256); p.text_bf = w.alloc<bf16>(ML * c.text_dim);
-  p.vid_bf = w.alloc<bf16>(M * c.vision_dim);
+  p.feat_bf = w.alloc<bf16>(MB * 256); p.text_bf = w.alloc<bf16>(ML * c.text_dim);
+  p.vid_bf = w.alloc<bf16>(MB * c.vision_dim);
   p.gn_partial = w.alloc<double>((int64_t)Bc * GN_CHUNKS * 2);
-  p.pad_mask = w.alloc<uint8_t>(M); p.text_mask = w.alloc<uint8_t>(ML);
+  p.pad_mask = w.alloc<uint8_t>(MB); p.text_mask = w.alloc<uint8_t>(ML);
   p.n_ids_cap = 64;
-  p.anchor_ids = w.alloc<long long>((int64_t)Bc * p.n_ids_cap); p.anchor_align = w.alloc<long long>(M);
+  p.anchor_ids = w.alloc<long long>((int64_t)B * p.n_ids_cap); p.anchor_align = w.alloc<long long>(MB);
 
   // ---- once-per-call conditioning GEMMs ----
-  p.g_cond = make_linear("cond.proj_feat", p.feat_bf, M, 256, e->wp_f, d, 256, EPI_AFFINE);
-  p.g_cond.P.bias = e->proj_b; p.g_cond.P.out_f32 = p.cond; p.g_cond.P.out_f32_ld = d;
+  p.g_cond = make_linear("cond.proj_feat", p.feat_bf, MB, 256, e->wp_f, d, 256, EPI_AFFINE);
+  p.g_cond.P.bias = e->proj_b; p.g_cond.P.out_f32 = p.condB; p.g_cond.P.out_f32_ld = d;
   p.g_mem = make_linear("cond.memory_proj", p.text_bf, ML, c.text_dim, e->wmem, d, 256, EPI_AFFINE);
   p.g_mem.P.bias = e->mem_b; p.g_mem.P.out_f32 = p.mem_base; p.g_mem.P.out_f32_ld = d;
-  p.g_vid = make_linear("cond.align_video", p.vid_bf, M, c.vision_dim, e->wvid, d, 256, EPI_AFFINE);
+  p.g_vid = make_linear("cond.align_video", p.vid_bf, MB, c.vision_dim, e->wvid, d, 256, EPI_AFFINE);
   p.g_vid.P.bias = e->vid_b; p.g_vid.P.out_f32 = p.vproj; p.g_vid.P.out_f32_ld = d;
 
   // ---- per-evaluation prologue ----
@@ -623,7 +667,8 @@ static void build_dit_plan(sab_engine* e, int Bc, int T, int L) {
       SAB_CHECK(o.q_c.BN == 256, "fused cross-attention needs BN=256 tiles");
       o.q_c.tag = "cross.wq+attn";
       o.q_c.P.out_bf16 = p.att; o.q_c.P.out_bf16_ld = d;
-      o.q_c.P.xa_kv = kvc_l; o.q_c.P.xa_kv_ld = kv_ld; o.q_c.P.xa_v_col0 = d; o.q_c.P.xa_Tk = L; o.q_c.P.xa_T = T;
+      o.q_c.P.xa_kv = kvc_l; o.q_c.P.xa_kv_ld = kv_ld; o.q_c.P.xa_v_col0 = d; o.q_c.P.xa_Tk = L;
+      o.q_c.P.xa_T = T * cand;   // query rows per K/V item: the cand sequences of a clip attend to the clip's text
       o.q_c.P.xa_mask = p.text_mask;
       o.q_c.P.xa_scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
       o.q_c.flops += 4.0 * Bc * c.n_heads * (double)T * L * 128;
@@ -683,11 +728,7 @@ static void rmsnorm_mod(sab_engine* e, const float* x, const float* w, const flo
 }
 
 static void attention(sab_engine* e, const AttnParams& ap, int items, int heads, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
-  }
+  ensure_dynamic_smem(attention_kernel, ATT_SMEM);
   const double fl = 4.0 * items * heads * (double)ap.Tq * ap.Tk * 128;
   if (ap.Tk <= XATT_MAX_TK && ap.k != ap.q) {   // a handful of text tokens: HBM-bound warp-per-row kernel
     mark(e, st, "sdpa.cross", fl, (double)items * ap.Tq * heads * 128 * 4.0);
@@ -703,20 +744,27 @@ static void attention(sab_engine* e, const AttnParams& ap, int items, int heads,
 
 static void launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& ap,
                                 int items, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-    configured = true;
-  }
+  ensure_dynamic_smem(attention_tc_kernel, ATC_SMEM);
   AttnTcParams p2 = ap;
   p2.items = items;
   const int n_work = ap.heads * items;
-  attention_tc_kernel<<<n_work < g_sm_count ? n_work : g_sm_count, ATC_THREADS, ATC_SMEM, st>>>(tq, tk, tv, p2);
+  attention_tc_kernel<<<n_work < sm_count() ? n_work : sm_count(), ATC_THREADS, ATC_SMEM, st>>>(tq, tk, tv, p2);
   SAB_CUDA(cudaGetLastError());
 }
 
+// algorithmic HBM bytes of one GEMM launch: operands once + every epilogue stream once (what a perfect kernel moves)
+static double gemm_bytes(const GemmOp& op) {
+  const GemmParams& P = op.P;
+  double per_elem = 0;
+  if (P.res) per_elem += 4;
+  if (P.out_f32) per_elem += 4;
+  if (P.out_bf16) per_elem += 2;
+  if (P.out_act) per_elem += 2;
+  const double n_out = (op.mode == EPI_SWIGLU) ? P.N / 2.0 : (double)P.N;
+  return op.in_bytes + op.rows * n_out * per_elem;
+}
 static void gemm(sab_engine* e, const GemmOp& op, cudaStream_t st) {
-  mark(e, st, op.tag, op.flops, 0);
+  mark(e, st, op.tag, op.flops, gemm_bytes(op));
   launch_gemm(op, st);
 }
 
@@ -731,12 +779,12 @@ struct FinalSpec {
 static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, cudaStream_t st) {
   DitPlan& p = *e->dit;
   const sab_config& c = e->cfg;
-  const int d = c.dim, Bc = p.Bc, T = p.T, L = p.L, NL = c.n_layers, H = c.n_heads;
+  const int d = c.dim, Bc = p.Bc, T = p.T, L = p.L, NL = c.n_layers, H = c.n_heads, cand = p.cand;
   const int M = (int)p.M;
   const float sl2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
 
   mark(e, st, "time_features_kernel");
-  time_features_kernel<<<256, 256, 0, st>>>(time_dev, Bc, d, L, p.tfreq, p.mem_base, p.mem_in);
+  time_features_kernel<<<256, 256, 0, st>>>(time_dev, Bc, cand, d, L, p.tfreq, p.mem_base, p.mem_in);
   gemm(e, p.g_t13, st);
   gemm(e, p.g_t2, st);
   mark(e, st, "silu_cast_kernel");
@@ -769,10 +817,10 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
     a.q = p.qkv; a.q_ld = 3 * d; a.q_col0 = 0;
     a.k = p.qkv; a.k_ld = 3 * d; a.k_col0 = d;
     a.v = p.qkv; a.v_ld = 3 * d; a.v_col0 = 2 * d;
-    a.o = p.att; a.o_ld = d; a.key_mask = p.pad_mask; a.Tq = T; a.Tk = T; a.scale_log2 = sl2;
+    a.o = p.att; a.o_ld = d; a.key_mask = p.pad_mask; a.Tq = T; a.Tk = T; a.scale_log2 = sl2; a.mask_div = cand;
     if (p.att_tc) {
       AttnTcParams tp{};
-      tp.o = p.att; tp.o_ld = d; tp.key_mask = p.pad_mask; tp.Tq = T; tp.Tk = T; tp.heads = H;
+      tp.o = p.att; tp.o_ld = d; tp.key_mask = p.pad_mask; tp.Tq = T; tp.Tk = T; tp.heads = H; tp.mask_div = cand;
       tp.q_col0 = 0; tp.k_col0 = d; tp.v_col0 = 2 * d; tp.scale_log2 = sl2; tp.v_lbo = ATC_KV_BYTES / 2; tp.v_sbo = 1024;
       mark(e, st, "sdpa.self", 4.0 * Bc * H * (double)T * T * 128, 0);
       launch_attention_tc(p.tm_att_q, p.tm_att_kv, p.tm_att_kv, tp, Bc, st);
@@ -787,6 +835,7 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
       x.k = p.kvc; x.k_ld = 2LL * d * NL; x.k_col0 = l * 2 * d;
       x.v = p.kvc; x.v_ld = 2LL * d * NL; x.v_col0 = l * 2 * d + d;
       x.o = p.att; x.o_ld = d; x.key_mask = p.text_mask; x.Tq = T; x.Tk = L; x.scale_log2 = sl2;
+      x.kv_div = cand; x.mask_div = cand;
       attention(e, x, Bc, H, st);
     }
     gemm(e, o.wo_c, st);
@@ -1052,6 +1101,7 @@ sab_engine::~sab_engine() {
 // C ABI
 // =====================================================================================================
 #define SAB_API_BEGIN try {
+#define SAB_API_BEGIN_E(e) try { SAB_CHECK((e) != nullptr, "null engine"); DeviceGuard _dg((e)->device);
 #define SAB_API_END                                   \
   }                                                   \
   catch (const std::exception& ex) {                  \
@@ -1072,11 +1122,11 @@ int sab_create(const sab_config* cfg, int device, sab_engine** out) {
   cudaError_t ce = cudaGetDeviceCount(&n_dev);
   SAB_CHECK(ce == cudaSuccess && n_dev > 0, "no CUDA device: the SAM-Audio B200 path has no CPU fallback (%s)",
             cudaGetErrorString(ce));
-  SAB_CUDA(cudaSetDevice(device));
+  SAB_CHECK(device >= 0 && device < n_dev && device < kMaxDevices, "bad device index %d", device);
+  DeviceGuard _dg(device);
   cudaDeviceProp prop;
   SAB_CUDA(cudaGetDeviceProperties(&prop, device));
   SAB_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  g_sm_count = prop.multiProcessorCount;
   if (const char* f = getenv("SAB_FORCE_CG")) g_force_cg = atoi(f);
   SAB_CHECK(cfg->dim % 128 == 0 && cfg->dim / cfg->n_heads == 128, "dim must be n_heads*128");
   SAB_CHECK(cfg->ffn_hidden % 64 == 0, "ffn_hidden must be a multiple of 64");
@@ -1102,7 +1152,7 @@ int sab_create(const sab_config* cfg, int device, sab_engine** out) {
 int sab_destroy(sab_engine* e) {
   SAB_API_BEGIN
   if (e) {
-    cudaSetDevice(e->device);
+    DeviceGuard _dg(e->device);
     cudaDeviceSynchronize();
     delete e;
   }
@@ -1111,7 +1161,7 @@ int sab_destroy(sab_engine* e) {
 
 int sab_load_weight(sab_engine* e, const char* name, const float* data, const int64_t* shape, int ndim, int is_device,
                     void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e && name && data, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   auto it = e->slots.find(name);
@@ -1142,14 +1192,22 @@ int sab_load_weight(sab_engine* e, const char* name, const float* data, const in
   SAB_API_END
 }
 
-int sab_finalize_weights(sab_engine* e, void* stream) {
-  SAB_API_BEGIN
+int sab_finalize_weights(sab_engine* e, int allow_missing, char* missing_out, int64_t missing_cap, void* stream) {
+  SAB_API_BEGIN_E(e)
   cudaStream_t st = (cudaStream_t)stream;
-  std::string missing;
+  std::string missing, all_missing;
   int n_missing = 0;
   for (auto& kv : e->slots)
-    if (!kv.second.loaded) { if (n_missing++ < 8) missing += kv.first + " "; }
-  SAB_CHECK(n_missing == 0, "Missing keys (%d): %s", n_missing, missing.c_str());
+    if (!kv.second.loaded) {
+      if (n_missing++ < 8) missing += kv.first + " ";
+      all_missing += kv.first + "\n";
+    }
+  SAB_CHECK(n_missing == 0 || allow_missing, "Missing keys (%d): %s", n_missing, missing.c_str());
+  if (missing_out && missing_cap > 0) {
+    const size_t n = std::min<size_t>(all_missing.size(), (size_t)missing_cap - 1);
+    memcpy(missing_out, all_missing.data(), n);
+    missing_out[n] = 0;
+  }
   const int d = e->cfg.dim;
   // constant video term for text-only prompts: LayerNorm(conv bias)   
   ln_vector_kernel<<<1, 256, 0, st>>>(e->vid_b, e->vid_ln_w, e->vid_ln_b, d, e->vid_const);
@@ -1163,52 +1221,64 @@ int sab_finalize_weights(sab_engine* e, void* stream) {
   SAB_API_END
 }
 
-int sab_prepare(sab_engine* e, int Bc, int T, int L, const float* features, const float* text_features,
+int sab_prepare(sab_engine* e, int B, int candidates, int T, int L, const float* features, const float* text_features,
                 const uint8_t* text_mask, const float* video_features, const int64_t* anchor_ids, int n_ids,
-                const int64_t* anchor_alignment, const uint8_t* audio_pad_mask, void* stream) {
-  SAB_API_BEGIN
-  SAB_CHECK(e && e->finalized, "weights not finalized");
-  SAB_CHECK(Bc > 0 && T > 0 && L > 0, "bad shape");
+                const int64_t* anchor_alignment, const uint8_t* audio_pad_mask, int flags, void* stream) {
+  SAB_API_BEGIN_E(e)
+  SAB_CHECK(e->finalized, "weights not finalized");
+  SAB_CHECK(B > 0 && candidates > 0 && T > 0 && L > 0, "bad shape");
+  SAB_CHECK(features && text_mask && audio_pad_mask, "null argument");
+  const bool no_text = (flags & SAB_PREP_NO_TEXT) != 0, no_anchor = (flags & SAB_PREP_NO_ANCHORS) != 0;
+  SAB_CHECK(no_text ? L == 1 : text_features != nullptr, "text_features missing (or SAB_PREP_NO_TEXT with L != 1)");
+  SAB_CHECK(no_anchor || (anchor_ids && anchor_alignment && n_ids > 0), "anchor tensors missing");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!e->dit || e->dit->Bc != Bc || e->dit->T != T || e->dit->L != L) {
+  if (!e->dit || e->dit->B != B || e->dit->cand != candidates || e->dit->T != T || e->dit->L != L) {
     SAB_CUDA(cudaStreamSynchronize(st));
     e->dit.reset();
-    build_dit_plan(e, Bc, T, L);
+    build_dit_plan(e, B, candidates, T, L);
   }
   DitPlan& p = *e->dit;
   const sab_config& c = e->cfg;
   const int d = c.dim;
-  SAB_CHECK(n_ids <= p.n_ids_cap, "too many anchors per clip (%d)", n_ids);
-  const long long M = p.M, ML = p.ML;
-  SAB_CUDA(cudaMemcpyAsync(p.pad_mask, audio_pad_mask, M, cudaMemcpyDeviceToDevice, st));
+  SAB_CHECK(n_ids <= p.n_ids_cap, "too many anchors per clip (%d > %d)", n_ids, p.n_ids_cap);
+  const long long M = p.M, MB = p.MB, ML = p.ML;
+  SAB_CUDA(cudaMemcpyAsync(p.pad_mask, audio_pad_mask, MB, cudaMemcpyDeviceToDevice, st));
   SAB_CUDA(cudaMemcpyAsync(p.text_mask, text_mask, ML, cudaMemcpyDeviceToDevice, st));
-  SAB_CUDA(cudaMemcpyAsync(p.anchor_ids, anchor_ids, (size_t)Bc * n_ids * 8, cudaMemcpyDeviceToDevice, st));
-  SAB_CUDA(cudaMemcpyAsync(p.anchor_align, anchor_alignment, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+  if (!no_anchor) {
+    SAB_CUDA(cudaMemcpyAsync(p.anchor_ids, anchor_ids, (size_t)B * n_ids * 8, cudaMemcpyDeviceToDevice, st));
+    SAB_CUDA(cudaMemcpyAsync(p.anchor_align, anchor_alignment, (size_t)MB * 8, cudaMemcpyDeviceToDevice, st));
+  }
   mark(e, st, "cast_bf16_kernel");
-  cast_bf16_kernel<<<512, 256, 0, st>>>(features, p.feat_bf, M * 256);
-  mark(e, st, "cast_bf16_kernel");
-  cast_bf16_kernel<<<64, 256, 0, st>>>(text_features, p.text_bf, ML * c.text_dim);
+  cast_bf16_kernel<<<512, 256, 0, st>>>(features, p.feat_bf, MB * 256);
   gemm(e, p.g_cond, st);
-  gemm(e, p.g_mem, st);
+  if (no_text) {   // model.py:170-172 with text_features=None: the memory is the time embedding alone
+    SAB_CUDA(cudaMemsetAsync(p.mem_base, 0, (size_t)ML * d * sizeof(float), st));
+  } else {
+    mark(e, st, "cast_bf16_kernel");
+    cast_bf16_kernel<<<64, 256, 0, st>>>(text_features, p.text_bf, ML * c.text_dim);
+    gemm(e, p.g_mem, st);
+  }
   const float* vproj = nullptr;
   if (video_features) {
     mark(e, st, "transpose_cast_kernel");
-    transpose_cast_kernel<<<1024, 256, 0, st>>>(video_features, c.vision_dim, T, M * c.vision_dim, p.vid_bf);
+    transpose_cast_kernel<<<1024, 256, 0, st>>>(video_features, c.vision_dim, T, MB * c.vision_dim, p.vid_bf);
     gemm(e, p.g_vid, st);
     vproj = p.vproj;
   }
   mark(e, st, "cond_finish_kernel");
-  cond_finish_kernel<<<(int)((M + 7) / 8), 256, 0, st>>>(p.cond, (int)M, d, T, vproj, e->vid_ln_w, e->vid_ln_b, e->vid_const,
-                                                        e->vid_gate, e->anchor_table,
+  cond_finish_kernel<<<(int)((M + 7) / 8), 256, 0, st>>>(p.cond, p.condB, (int)M, d, T, candidates, vproj, e->vid_ln_w,
+                                                        e->vid_ln_b, e->vid_const, e->vid_gate, e->anchor_table,
                                                         reinterpret_cast<const long long*>(p.anchor_ids), n_ids,
-                                                        reinterpret_cast<const long long*>(p.anchor_align), e->anchor_gate);
+                                                        reinterpret_cast<const long long*>(p.anchor_align), e->anchor_gate,
+                                                        (flags & SAB_PREP_NO_VIDEO_TERM) ? 0 : 1, no_anchor ? 0 : 1);
   SAB_CUDA(cudaGetLastError());
   SAB_API_END
 }
 
 int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float* velocity, void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e && e->dit, "sab_prepare must be called first");
+  SAB_CHECK(e->dit->cand == 1, "sab_dit_forward takes per-sequence times: prepare with candidates == 1");
   cudaStream_t st = (cudaStream_t)stream;
   DitPlan& p = *e->dit;
   mark(e, st, "cast_bf16_kernel");
@@ -1219,7 +1289,7 @@ int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float*
 }
 
 int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e && e->dit, "sab_prepare must be called first");
   SAB_CHECK(n_steps >= 1 && 2 * n_steps <= 64, "n_steps out of range");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1326,8 +1396,10 @@ static void run_codec(sab_engine* e, CodecPlan& cp, int items, const float* wav_
         op.P.n_items = items;
         if (&s.op == cp.enc_out) op.P.out_f32 = out;
         const long long tiles = (long long)items * op.P.tiles_per_item * op.P.n_tiles_n;
-        op.grid = (int)std::min<long long>(tiles, g_sm_count / op.cg) * op.cg;
+        op.grid = (int)std::min<long long>(tiles, sm_count() / op.cg) * op.cg;
         op.flops = s.op.flops * (double)items / (double)cp.items;
+        op.rows = s.op.rows * (double)items / (double)cp.items;
+        op.in_bytes = s.op.in_bytes * (double)items / (double)cp.items;   // (the weight share is negligible here)
         gemm(e, op, st);
       }
     }
@@ -1340,12 +1412,14 @@ static int codec_chunk(const sab_engine* e, long long S_samples, bool decoder) {
   // encoder, ~0.85 GB per 10 s waveform in the decoder; keep a chunk's workspace near 12 GB
   (void)e;
   const double per_item = (double)S_samples / 480000.0 * (decoder ? 0.85e9 : 0.56e9);
-  int n = (int)(12e9 / per_item);
+  double budget = 12e9;
+  if (const char* b = getenv("SAB_CODEC_CHUNK_BYTES")) budget = atof(b);   // tests force small chunks through this
+  int n = (int)(budget / per_item);
   return n < 1 ? 1 : (n > 64 ? 64 : n);
 }
 
 int sab_encode(sab_engine* e, const float* wav, int B, int64_t S, float* features, void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e && e->finalized, "weights not finalized");
   cudaStream_t st = (cudaStream_t)stream;
   long long hop = 1;
@@ -1363,15 +1437,16 @@ int sab_encode(sab_engine* e, const float* wav, int B, int64_t S, float* feature
 }
 
 int sab_decode(sab_engine* e, const float* latent, int Bc, int T, float* wav, void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e && e->finalized, "weights not finalized");
   cudaStream_t st = (cudaStream_t)stream;
   long long hop = 1;
   for (int i = 0; i < e->cfg.codec_n_rates; ++i) hop *= e->cfg.codec_decoder_rates[i];
   const long long S = (long long)T * hop;
   const int items = 2 * Bc;
-  int chunk = std::min(items, codec_chunk(e, S, true));
-  if (chunk > 1) chunk &= ~1;  // whole clips per chunk
+  // whole clips per chunk: items (2b, 2b+1) = (target, residual) come from the two halves of latent row b, so a chunk
+  // is always an even number of items, at least one clip (a single-item chunk would decode the target half twice)
+  int chunk = std::min(items, std::max(2, codec_chunk(e, S, true) & ~1));
   CodecPlan* cp = get_dec_plan(e, chunk, T);
   const int cz = e->cfg.codec_codebook_dim;
   for (int i0 = 0; i0 < items; i0 += chunk) {
@@ -1399,7 +1474,7 @@ int64_t sab_workspace_bytes(sab_engine* e) {
 }
 
 int sab_profile(sab_engine* e, int enable, void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e, "null engine");
   SAB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   e->prof = enable != 0;
@@ -1409,7 +1484,7 @@ int sab_profile(sab_engine* e, int enable, void* stream) {
 
 // JSON: {"tag": {"launches": n, "ms": t, "flops": f, "bytes": b}, ...} aggregated since sab_profile(e, 1).
 int sab_profile_report(sab_engine* e, char* buf, int64_t cap, void* stream) {
-  SAB_API_BEGIN
+  SAB_API_BEGIN_E(e)
   SAB_CHECK(e && buf && cap > 2, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = e->prof_recs.size();
@@ -1447,11 +1522,6 @@ int sab_profile_report(sab_engine* e, char* buf, int64_t cap, void* stream) {
 int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, float* c, int bn, int bk, int cg,
                   void* stream) {
   SAB_API_BEGIN
-  if (!g_sm_count) {
-    cudaDeviceProp prop;
-    SAB_CUDA(cudaGetDeviceProperties(&prop, 0));
-    g_sm_count = prop.multiProcessorCount;
-  }
   RunList rl;
   SAB_CHECK(K % bk == 0, "K must be a multiple of bk");
   rl.add(0, 0, 0, K / bk);
@@ -1464,7 +1534,7 @@ int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, f
 int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, const void* k, const void* v,
                        const uint8_t* key_mask, void* o, void* stream) {
   SAB_API_BEGIN
-  SAB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  ensure_dynamic_smem(attention_kernel, ATT_SMEM);
   AttnParams a{};
   const long long ld = (long long)heads * 128;
   a.q = (const bf16*)q; a.q_ld = ld; a.k = (const bf16*)k; a.k_ld = ld; a.v = (const bf16*)v; a.v_ld = ld;
@@ -1484,11 +1554,6 @@ int sab_test_attention_tc(int items, int heads, int T, const void* q, const void
                           const uint8_t* key_mask, void* o, int v_lbo, int v_sbo, void* stream) {
   SAB_API_BEGIN
   SAB_CHECK(T <= 256, "tcgen05 attention handles T <= 256");
-  if (!g_sm_count) {
-    cudaDeviceProp prop;
-    SAB_CUDA(cudaGetDeviceProperties(&prop, 0));
-    g_sm_count = prop.multiProcessorCount;
-  }
   const long long ld = (long long)heads * 128;
   CUtensorMap tq = make_tmap_3d(q, ld, T, items, ld, (int64_t)T * ld, 64, 128);
   CUtensorMap tk = make_tmap_3d(k, ld, T, items, ld, (int64_t)T * ld, 64, 256);

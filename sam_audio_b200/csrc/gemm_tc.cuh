@@ -72,7 +72,8 @@ struct GemmParams {
   const float2* rope; int rope_T; int use_rope; float eps;
   // fused cross-attention to a few text tokens (QKV mode, all heads are queries): instead of writing the normalised
   // queries, the epilogue attends to K/V [items*Tk, ld] (head-major columns; V at +xa_v_col0) and writes O
-  const __nv_bfloat16* xa_kv; long long xa_kv_ld; int xa_v_col0; int xa_Tk; int xa_T;
+  const __nv_bfloat16* xa_kv; long long xa_kv_ld; int xa_v_col0; int xa_Tk;
+  int xa_T;                 // query rows per K/V item (T x candidates: the candidates of a clip share its text K/V)
   const uint8_t* xa_mask;   // [items, Tk] or null
   float xa_scale_log2;
 };

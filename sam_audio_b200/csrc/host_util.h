@@ -129,6 +129,8 @@ struct GemmOp {
   int grid = 0;
   const char* tag = "";
   double flops = 0;  // algorithmic 2*M*N*K
+  double in_bytes = 0;   // algorithmic operand bytes: every A element once + the packed weight once
+  double rows = 0;       // output rows (for the epilogue's output / residual bytes)
 };
 
 }  // namespace sab

@@ -79,13 +79,20 @@ class SAMAudio(torch.nn.Module):
         self.register_buffer("_anchor", torch.zeros(1), persistent=False)
 
     # ------------------------------------------------------------------ loading
+    # keyword arguments huggingface_hub.ModelHubMixin.from_pretrained consumes itself (the reference inherits them,
+    # base.py:17-45): they go to snapshot_download, never to the constructor
+    _HUB_KWARGS = ("force_download", "resume_download", "proxies", "token", "cache_dir", "local_files_only", "revision")
+
     @classmethod
     def from_pretrained(cls, model_id: str, map_location: str = "cpu", strict: bool = True, **model_kwargs):
+        hub = {k: model_kwargs.pop(k) for k in cls._HUB_KWARGS if k in model_kwargs}
         if os.path.isdir(model_id):
             root = model_id
         else:
             from huggingface_hub import snapshot_download
-            root = snapshot_download(repo_id=model_id, revision=cls.revision)
+            hub.setdefault("revision", cls.revision)
+            hub.pop("resume_download", None)            # accepted for compatibility; deprecated upstream
+            root = snapshot_download(repo_id=model_id, **hub)
         with open(os.path.join(root, "config.json")) as f:
             config = json.load(f)
         ctor_kwargs = {}
@@ -106,17 +113,36 @@ class SAMAudio(torch.nn.Module):
         loaded elsewhere; everything else must match exactly (checked by the engine)."""
         sd = {k: v for k, v in state_dict.items() if not _SKIP_PREFIXES.match(k)}
         self._state = fold_weight_norm(sd)
+        self._strict = bool(strict)
         if self._engine is not None:
-            self._push_weights()
+            return self._push_weights()
+        # the engine (and with it the key check) is created on the first .cuda(); until then nothing is known
+        return torch.nn.modules.module._IncompatibleKeys([], [])
 
     def _push_weights(self):
+        """strict=True: any unexpected or missing key raises (reference model.py:356-359).  strict=False: unexpected
+        keys are skipped, missing ones keep their zero initialisation, and both lists are returned
+        (torch's _IncompatibleKeys) — the codec's key names are an assumption (dacvae source is absent), so a real
+        checkpoint that deviates is reported key by key instead of failing on the first one."""
         assert self._engine is not None and self._state is not None
+        strict = getattr(self, "_strict", True)
+        unexpected: List[str] = []
         try:
             for k, v in self._state.items():
-                self._engine.load_weight(k, v)
-            self._engine.finalize()
+                try:
+                    self._engine.load_weight(k, v)
+                except RuntimeError as exc:
+                    if strict or "unexpected weight" not in str(exc):
+                        raise
+                    unexpected.append(k)
+            missing = self._engine.finalize(allow_missing=not strict)
         except RuntimeError as exc:
-            raise RuntimeError(f"load_state_dict: {exc}") from exc
+            hint = ""
+            if "audio_codec." in str(exc):
+                hint = (" — the audio_codec.* names follow the Descript-DAC layout that `dacvae` derives from; "
+                        "load with strict=False to list every unmatched key")
+            raise RuntimeError(f"load_state_dict: {exc}{hint}") from exc
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
@@ -163,42 +189,51 @@ class SAMAudio(torch.nn.Module):
         B, S = wav.shape
         T = S // self.cfg.audio_codec.hop_length
         feats = torch.empty(B, T, 2 * self.cfg.audio_codec.codebook_dim, device=wav.device, dtype=torch.float32)
-        eng.encode(wav, feats)
+        with torch.cuda.device(wav.device):
+            eng.encode(wav, feats)
         return feats
 
-    @staticmethod
-    def _repeat(t: Optional[torch.Tensor], c: int):
-        if t is None or c == 1:
-            return t
-        return t.repeat_interleave(c, dim=0)
-
     def _install_conditioning(self, audio_features, text_features, text_mask, masked_video_features,
-                              anchor_ids, anchor_alignment, audio_pad_mask):
+                              anchor_ids, anchor_alignment, audio_pad_mask, candidates: int = 1, flags: int = 0):
+        """Per-clip tensors; the `candidates` sequences of a clip share them inside the engine
+        (reference _repeat_for_reranking, model.py:193-203, without materialising the copies)."""
         eng = self._ensure_engine()
-        Bc, T, _ = audio_features.shape
-        L = text_features.shape[1]
+        B, T, _ = audio_features.shape
+        dev = audio_features.device
+        if text_features is None:                      # reference forward(text_features=None): time-only memory
+            flags |= _capi.PREP_NO_TEXT
+            L = 1
+        else:
+            L = text_features.shape[1]
+            text_features = text_features.float().contiguous()
+        if anchor_ids is None:                         # reference EmbedAnchors returns its input (model.py:57-58)
+            flags |= _capi.PREP_NO_ANCHORS
+        else:
+            anchor_ids = anchor_ids.long().contiguous()
+            anchor_alignment = anchor_alignment.long().contiguous()
         if audio_pad_mask is None:
-            audio_pad_mask = torch.ones(Bc, T, dtype=torch.bool, device=audio_features.device)
+            audio_pad_mask = torch.ones(B, T, dtype=torch.bool, device=dev)
         if text_mask is None:
-            text_mask = torch.ones(Bc, L, dtype=torch.bool, device=audio_features.device)
+            text_mask = torch.ones(B, L, dtype=torch.bool, device=dev)
         vid = None if masked_video_features is None else masked_video_features.float().contiguous()
-        eng.prepare(Bc, T, L, audio_features.float().contiguous(), text_features.float().contiguous(),
-                    text_mask.to(torch.uint8).contiguous(), vid, anchor_ids.long().contiguous(),
-                    anchor_alignment.long().contiguous(), audio_pad_mask.to(torch.uint8).contiguous())
+        with torch.cuda.device(dev):
+            eng.prepare(B, candidates, T, L, audio_features.float().contiguous(), text_features,
+                        text_mask.to(torch.uint8).contiguous(), vid, anchor_ids, anchor_alignment,
+                        audio_pad_mask.to(torch.uint8).contiguous(), flags)
 
     @torch.inference_mode()
     def forward(self, noisy_audio, audio_features, text_features, time, masked_video_features=None,
                 text_mask=None, anchor_ids=None, anchor_alignment=None, audio_pad_mask=None):
         """One ODE function evaluation (reference model.py:130-180)."""
         eng = self._ensure_engine()
-        Bc, T, _ = audio_features.shape
-        if anchor_ids is None:
-            anchor_ids = torch.tensor([[0, 3]], device=noisy_audio.device).repeat(Bc, 1)
-            anchor_alignment = torch.zeros(Bc, T, dtype=torch.long, device=noisy_audio.device)
+        # None arguments mean what they mean in the reference: no video term (align.py:41-42), no anchor term
+        # (model.py:57-58), time-only memory (model.py:170-172).  separate() never passes None.
+        flags = _capi.PREP_NO_VIDEO_TERM if masked_video_features is None else 0
         self._install_conditioning(audio_features, text_features, text_mask, masked_video_features,
-                                   anchor_ids, anchor_alignment, audio_pad_mask)
+                                   anchor_ids, anchor_alignment, audio_pad_mask, flags=flags)
         out = torch.empty_like(noisy_audio, dtype=torch.float32)
-        eng.dit_forward(noisy_audio.float().contiguous(), time.float().contiguous(), out)
+        with torch.cuda.device(noisy_audio.device):
+            eng.dit_forward(noisy_audio.float().contiguous(), time.float().contiguous(), out)
         return out
 
     @torch.inference_mode()
@@ -225,19 +260,18 @@ class SAMAudio(torch.nn.Module):
         anchor_ids, anchor_alignment, pad_mask = batch.anchor_ids, batch.anchor_alignment, batch.audio_pad_mask
         if predict_spans and getattr(self, "span_predictor", None) is not None and batch.anchors is None:
             batch = self.predict_spans(batch, feats, batch.audio_pad_mask)
-        self._install_conditioning(self._repeat(feats, c), self._repeat(text_features, c),
-                                   self._repeat(text_mask, c), self._repeat(video, c),
-                                   self._repeat(anchor_ids, c), self._repeat(anchor_alignment, c),
-                                   self._repeat(pad_mask, c))
+        self._install_conditioning(feats, text_features, text_mask, video, anchor_ids, anchor_alignment, pad_mask,
+                                   candidates=c)
         if noise is None:
             noise = torch.randn(B * c, T, C2, device=feats.device, dtype=torch.float32)
         noise = noise.to(device=feats.device, dtype=torch.float32).contiguous()
         latent = torch.empty_like(noise)
-        eng.solve(noise, n_steps, latent)
-
         hop = self.cfg.audio_codec.hop_length
         wavs = torch.empty(B * c, 2, T * hop, device=feats.device, dtype=torch.float32)
-        eng.decode(latent, B * c, T, wavs)
+        with torch.cuda.device(feats.device):
+            eng.solve(noise, n_steps, latent)
+            eng.decode(latent, B * c, T, wavs)
+        self._last_latent = latent                                          # diagnostics (parity tests, bench gate)
 
         sizes = (batch.sizes * hop).int()                                   # codec.py:91-97
         tgt = self.unbatch(wavs[:, 0].view(B, c, -1), sizes)

@@ -70,13 +70,21 @@ class T5TextEncoder(torch.nn.Module):
         self.pad_mode = cfg.pad_mode
         self.max_length = cfg.max_length
         self.random_init = False
-        try:
-            self.model = transformers.T5EncoderModel.from_pretrained(cfg.name, local_files_only=True)
-            self.tokenizer = transformers.AutoTokenizer.from_pretrained(cfg.name, local_files_only=True)
-        except Exception as exc:  # no checkpoint on disk
+        exc = None
+        # the local cache first (no network round trip), then a normal download like the reference does
+        # (text_encoder.py:13-14); only if both fail is the checkpoint really unavailable
+        for local_only in (True, False):
+            try:
+                self.model = transformers.T5EncoderModel.from_pretrained(cfg.name, local_files_only=local_only)
+                self.tokenizer = transformers.AutoTokenizer.from_pretrained(cfg.name, local_files_only=local_only)
+                exc = None
+                break
+            except Exception as err:  # not cached / no network
+                exc = err
+        if exc is not None:
             if not allow_random_init:
                 raise RuntimeError(
-                    f"text encoder '{cfg.name}' is not available locally ({type(exc).__name__}); "
+                    f"text encoder '{cfg.name}' is neither cached locally nor downloadable ({type(exc).__name__}); "
                     "pass allow_random_init=True for synthetic benchmarking") from exc
             t5 = transformers.T5Config(vocab_size=32128, d_model=cfg.dim, d_kv=64, d_ff=3072, num_layers=12,
                                        num_heads=12, relative_attention_num_buckets=32, dropout_rate=0.0,

@@ -102,12 +102,25 @@ def test_dit_evaluation_vs_reference_golden(tiny_model, golden_dir):
     """SAMAudio.forward (ragged pad mask, text mask, anchors, with and without video) vs the reference's
     own SAMAudio.forward output (tests/golden/samaudio_forward_tiny.pt)."""
     g = torch.load(os.path.join(golden_dir, "samaudio_forward_tiny.pt"))
-    for tag, vid in (("video", g["video"]), ("novideo", None)):
+    for tag, vid in (("video", g["video"]), ("novideo", torch.zeros_like(g["video"]))):
         out = tiny_model.forward(g["noisy"].cuda(), g["feats"].cuda(), g["text"].cuda(), g["time"].cuda(),
-                                 masked_video_features=None if vid is None else vid.cuda(),
+                                 masked_video_features=vid.cuda(),
                                  text_mask=g["text_mask"].cuda(), anchor_ids=g["anchor_ids"].cuda(),
                                  anchor_alignment=g["anchor_alignment"].cuda(), audio_pad_mask=g["pad_mask"].cuda())
         assert rel_l2(out.cpu(), g["out"][tag]) < 2e-2, tag
+
+
+def test_dit_evaluation_none_arguments_vs_reference_golden(tiny_model, golden_dir):
+    """The `None` cases of SAMAudio.forward mean what they mean in the reference: no video term (align.py:41-42),
+    no anchor term (model.py:57-58), time-only memory (model.py:170-172) — golden = the reference's own output."""
+    g = torch.load(os.path.join(golden_dir, "samaudio_forward_tiny.pt"))
+    out = tiny_model.forward(g["noisy"].cuda(), g["feats"].cuda(), g["text"].cuda(), g["time"].cuda(),
+                             text_mask=g["text_mask"].cuda(), audio_pad_mask=g["pad_mask"].cuda())
+    assert rel_l2(out.cpu(), g["out"]["none_video_anchors"]) < 2e-2
+    out = tiny_model.forward(g["noisy"].cuda(), g["feats"].cuda(), None, g["time"].cuda(), audio_pad_mask=g["pad_mask"].cuda())
+    assert rel_l2(out.cpu(), g["out"]["none_text"]) < 2e-2
+    # and they differ from the zeros-video / <null>-anchor path separate() takes
+    assert rel_l2(g["out"]["none_video_anchors"], g["out"]["novideo"]) > 1e-3
 
 
 @pytest.mark.parametrize("L", [1, 8, 12, 20])
@@ -226,8 +239,10 @@ def test_codec_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
     assert rel_l2(out.cpu(), ref_w) < 3e-2 and float(out.abs().max()) <= 1.0
 
 
-@pytest.mark.parametrize("cand", [1, 2])
+@pytest.mark.parametrize("cand", [1, 2, 8])
 def test_separate_vs_reference_golden(tiny_model, golden_dir, cand):
+    """separate() vs the reference's own separate() (candidates 1, 2 and 8: the candidates of a clip share the clip's
+    conditioning inside the engine instead of the reference's expand/reshape copies, model.py:193-203)."""
     from sam_audio_b200 import SAMAudioProcessor
     from sam_audio_b200.synthetic import synthetic_clip, synthetic_descriptions
     g = torch.load(os.path.join(golden_dir, "separate_tiny.pt"))
@@ -240,6 +255,24 @@ def test_separate_vs_reference_golden(tiny_model, golden_dir, cand):
     for ours, ref in zip(list(out.target) + list(out.residual), list(r["target"]) + list(r["residual"])):
         assert ours.shape == ref.shape                      # lengths = sizes*1920, bit-exact
         assert snr_db(ours.cpu(), ref) > 30.0
+    # every candidate's latent (not only the returned candidate 0) against the reference pipeline's ODE state
+    assert rel_l2(tiny_model._last_latent.cpu(), r["latent"]) < 2e-2
+
+
+def test_decode_small_chunks_equal_unchunked(tiny_model, monkeypatch):
+    """Long clips are decoded in chunks of whole clips (target + residual halves of one latent row): forcing the
+    smallest chunk (one clip = two waveforms) must reproduce the unchunked decode bit for bit."""
+    lat = torch.randn(3, 12, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    eng = tiny_model._ensure_engine()
+    full = torch.empty(3, 2, 12 * 1920, device="cuda")
+    eng.decode(lat, 3, 12, full)
+    monkeypatch.setenv("SAB_CODEC_CHUNK_BYTES", "1e6")      # < one waveform's workspace: chunk clamps to one clip
+    small = torch.empty_like(full)
+    eng.decode(lat, 3, 12, small)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("SAB_CODEC_CHUNK_BYTES")
+    assert torch.equal(full, small)
+    assert not torch.equal(small[:, 0], small[:, 1])        # residual is not a copy of the target
 
 
 def test_separate_with_anchors_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
@@ -334,6 +367,14 @@ def test_missing_or_unknown_weights_fail_loudly(tiny_cfg, tiny_sd):
     m2.load_state_dict(sd2)
     with pytest.raises(RuntimeError, match="unexpected weight"):
         m2._ensure_engine()
+    # strict=False: the same two defects are reported, not raised (torch's _IncompatibleKeys)
+    m4 = SAMAudio(tiny_cfg, text_encoder=SyntheticTextEncoder()).cuda()
+    sd4 = dict(sd2)
+    sd4.pop("audio_codec.decoder.model.0.bias")
+    m4.load_state_dict(sd4, strict=False)
+    m4._ensure_engine()
+    res = m4._push_weights()
+    assert res.unexpected_keys == ["transformer.bogus.weight"] and res.missing_keys == ["audio_codec.decoder.model.0.bias"]
     m3 = SAMAudio(tiny_cfg, text_encoder=SyntheticTextEncoder())
     m3.load_state_dict(tiny_sd)
     with pytest.raises(RuntimeError, match="B200 only"):

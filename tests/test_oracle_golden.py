@@ -24,6 +24,13 @@ def test_samaudio_forward_matches_reference_golden(golden_dir, tiny_cfg, tiny_sd
         out = restate.samaudio_forward(tiny_sd, tiny_cfg, g["noisy"], g["feats"], g["text"], g["time"], vid,
                                        g["text_mask"], g["anchor_ids"], g["anchor_alignment"], g["pad_mask"])
         assert rel_l2(out, g["out"][tag]) < 2e-5, tag
+    # the reference's `None` arguments: no video term, no anchor term, time-only memory (model.py:57-58,170-172)
+    out = restate.samaudio_forward(tiny_sd, tiny_cfg, g["noisy"], g["feats"], g["text"], g["time"], None,
+                                   g["text_mask"], None, None, g["pad_mask"])
+    assert rel_l2(out, g["out"]["none_video_anchors"]) < 2e-5
+    out = restate.samaudio_forward(tiny_sd, tiny_cfg, g["noisy"], g["feats"], None, g["time"], None, None, None, None,
+                                   g["pad_mask"])
+    assert rel_l2(out, g["out"]["none_text"]) < 2e-5
 
 
 def test_processor_restatement_matches_reference_golden(golden_dir):
@@ -56,7 +63,7 @@ def test_midpoint_solver_is_32_evaluations_at_exact_times():
 
 
 def test_separate_control_flow_matches_reference_golden(golden_dir, tiny_cfg, tiny_sd):
-    """encode -> 32 evaluations -> decode -> unbatch, candidates 1 (reference pipeline output)."""
+    """encode -> 32 evaluations -> decode -> unbatch, candidates 1 and 8 (reference pipeline output)."""
     g = torch.load(os.path.join(golden_dir, "separate_tiny.pt"))
     auds = [synthetic.synthetic_clip(i, n) for i, n in enumerate(g["lens"])]
     aud, ws = restate.batch_audio(auds)
@@ -64,12 +71,13 @@ def test_separate_control_flow_matches_reference_golden(golden_dir, tiny_cfg, ti
     mask = restate.mask_from_sizes(sizes)
     ids, al = restate.process_anchors(None, mask, 1920, 48000)
     tf, tm = synthetic.synthetic_text_features(synthetic.synthetic_descriptions(2))
-    r = g["results"][1]
-    tgt, res, lat = restate.separate(tiny_sd, tiny_cfg, aud, mask, sizes, tf, tm, ids, al, r["noise"],
-                                     return_latent=True)
-    assert rel_l2(lat, r["latent"]) < 1e-4
-    for a, b in zip(tgt + res, list(r["target"]) + list(r["residual"])):
-        assert a.shape == b.shape and rel_l2(a, b) < 1e-4
+    for cand in (1, 8):                                   # 8 = BASELINE config 4's reranking_candidates
+        r = g["results"][cand]
+        tgt, res, lat = restate.separate(tiny_sd, tiny_cfg, aud, mask, sizes, tf, tm, ids, al, r["noise"],
+                                         candidates=cand, return_latent=True)
+        assert lat.shape[0] == 2 * cand and rel_l2(lat, r["latent"]) < 1e-4
+        for a, b in zip(tgt + res, list(r["target"]) + list(r["residual"])):
+            assert a.shape == b.shape and rel_l2(a, b) < 1e-4
 
 
 def test_codec_shapes_and_hop(tiny_cfg, tiny_sd):
