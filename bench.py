@@ -290,7 +290,9 @@ def run_gpu(args):
     import __graft_entry__ as g
     world, rank, local = _dist_setup(args.gpus)
     if rank == 0:
-        g.build()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # stdout carries the ONE JSON line
+            g.build()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

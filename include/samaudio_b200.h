@@ -155,6 +155,11 @@ int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, cons
  * defaults of the MN-major V descriptor. */
 int sab_test_attention_tc(int items, int heads, int T, const void* q, const void* k, const void* v,
                           const uint8_t* key_mask, void* o, int v_lbo, int v_sbo, void* stream);
+/* second-generation kernel (attention_tc2.cuh): shift_log2 >= 0 = single-pass softmax with that logit bound,
+ * < 0 = exact two-pass; poly = pairs of every 8 exponentials evaluated on the FMA pipe (0..4, < 0: default);
+ * trace: null, or a device buffer of 8 x 32 x 8 int64 that CTA 0 fills with clock64() stamps (tools/attn_trace.py). */
+int sab_test_attention_tc2(int items, int heads, int T, const void* q_bf16, const void* k_bf16, const void* v_bf16,
+                           const uint8_t* key_mask, void* o_bf16, float shift_log2, int poly, long long* trace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,15 +14,16 @@ template <int kVecPerLane>  // d = kVecPerLane * 128
 __global__ void __launch_bounds__(256, (kVecPerLane > 24) ? 1 : 2)
 rmsnorm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_ld, int rows_per_item,
-                   __nv_bfloat16* __restrict__ out, int M, float eps) {
+                   __nv_bfloat16* __restrict__ out, int M, float eps, int reverse) {
   // Single pass: the row lives in registers (kVecPerLane float4 per lane, 88 floats at d = 2816), so x is read from
   // HBM exactly once (6 B per element: 4 read + 2 written).  All of a lane's loads are issued back to back
   // (streaming, no L1 allocation) before the reduction; 2 CTAs x 8 warps per SM keep >100 KB of loads in flight,
   // several times the bandwidth-latency product.  The two-pass version re-read every row (10 B per element).
   constexpr int d = kVecPerLane * 128;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
+  if (reverse) row = M - 1 - row;      // last rows first: the producer wrote them last, they are still in L2
   const float* xr = x + (long long)row * d + lane * 4;
   float4 v[kVecPerLane];
 #pragma unroll

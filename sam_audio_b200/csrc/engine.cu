@@ -15,6 +15,7 @@
 #include "host_util.h"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc2.cuh"
 #include "elementwise.cuh"
 #include "codec_kernels.cuh"
 
@@ -41,14 +42,15 @@ static int sm_count() {   // of the current device
   }
   return cached[d];
 }
-// cudaFuncSetAttribute is per device: once per (kernel instantiation, device)
-template <typename K>
-static void ensure_dynamic_smem(K kern, int smem) {
-  static bool configured[kMaxDevices] = {false};
+// cudaFuncSetAttribute is per device: once per (kernel, device).  Keyed by the function ADDRESS: all instantiations
+// of one kernel template share a function-pointer type, so a per-type static would configure only the first one.
+static void ensure_dynamic_smem(const void* kern, int smem) {
+  static std::unordered_map<const void*, std::array<bool, kMaxDevices>> configured;
   const int d = cur_device();
-  if (!configured[d]) {
+  auto& flags = configured[kern];   // value-initialised to all false on first use
+  if (!flags[d]) {
     SAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[d] = true;
+    flags[d] = true;
   }
 }
 // every entry point runs on its engine's device whatever the caller's current device is, and restores it
@@ -69,7 +71,7 @@ template <int BN, int BK, int MODE, int CG, bool B2B = false>
 static void launch_gemm_inst(const GemmOp& op, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, BK, MODE, CG, B2B>;
   constexpr int smem = GemmSmem<BN, BK, CG, B2B>::kTotal;
-  ensure_dynamic_smem(kern, smem);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
   if (CG == 1) {
     kern<<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, op.b2b ? op.tmW : op.tmB, op.P);
   } else {
@@ -240,6 +242,10 @@ struct Slot {
 struct LayerW {
   bf16 *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *w13, *w2;
   float *qn, *kn, *qn_c, *kn_c, *attn_norm, *ffn_norm;
+  float* qn_scaled = nullptr;   // q_norm.weight * log2(e)/sqrt(hd): the QKV epilogue emits q in the softmax's log2 domain
+  // self-attention logit bound (log2 domain) from the QK-norm weights: |q.k| / sqrt(hd) <= sqrt(hd) max|w_q| max|w_k|
+  // (RMSNorm'd vectors have norm <= sqrt(hd) max|w|, RoPE preserves norms); < 0: unknown -> exact two-pass softmax
+  float att_shift_log2 = -1.f;
 };
 
 struct ConvLayer {   // a multi-channel codec conv lowered to the GEMM
@@ -455,6 +461,7 @@ static void register_weights(sab_engine* e) {
     reg_linear(e, p + ".attention.wv.weight", d, d, nullptr, ROW_HEADS, H, W.wqkv, 2 * d, d);
     reg_linear(e, p + ".attention.wo.weight", d, d, &W.wo);
     reg_f32(e, p + ".attention.q_norm.weight", {128}, &W.qn);
+    W.qn_scaled = e->wpool.alloc<float>(128, true);
     reg_f32(e, p + ".attention.k_norm.weight", {128}, &W.kn);
     reg_linear(e, p + ".cross_attention.wq.weight", d, d, &W.wq_c, ROW_HEADS, H);
     W.wkv_c = e->wkv_c_all + (int64_t)l * 2 * d * d;
@@ -563,6 +570,7 @@ struct DitPlan {
   GemmOp g_t13, g_t2, g_tb, g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid, g_kvc_all;
   std::vector<LayerOps> lay;
   CUtensorMap tm_att_q, tm_att_kv;   // fused-QKV buffer viewed as (3d cols, T rows, Bc items): box 64x128 / 64x256
+  CUtensorMap tm_att_o;              // attention output viewed as (d cols, T rows, Bc items): box 64x128 (TMA store)
   bool att_tc = false;               // tcgen05 self-attention usable (T <= 256)
   bool xa_fused = false;             // cross-attention folded into the cross.wq GEMM epilogue (L <= XA_MAX_TK)
   double flops_per_eval = 0;
@@ -653,7 +661,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
     bf16* kvc_l = p.kvc + (long long)l * 2 * d;
     o.qkv = make_linear("attention.qkv", p.xn, M, d, W.wqkv, 3 * d, 256, EPI_QKV);
     o.qkv.P.out_bf16 = p.qkv; o.qkv.P.out_bf16_ld = 3 * d;
-    o.qkv.P.qnorm_w = W.qn; o.qkv.P.knorm_w = W.kn; o.qkv.P.n_q_end = d; o.qkv.P.n_k_end = 2 * d;
+    o.qkv.P.qnorm_w = W.qn_scaled; o.qkv.P.knorm_w = W.kn; o.qkv.P.n_q_end = d; o.qkv.P.n_k_end = 2 * d;
     o.qkv.P.rope = e->rope; o.qkv.P.rope_T = T; o.qkv.P.use_rope = 1; o.qkv.P.eps = c.norm_eps;
     o.wo = make_linear("attention.wo", p.att, M, d, W.wo, d, 256, EPI_AFFINE);
     o.wo.P.gate = mod_l + 2 * d; o.wo.P.gate_ld = 6 * d; o.wo.P.gate_div = T;
@@ -693,6 +701,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
   if (p.att_tc) {
     p.tm_att_q = make_tmap_3d(p.qkv, 3LL * d, T, Bc, 3LL * d, (int64_t)T * 3 * d, 64, 128);
     p.tm_att_kv = make_tmap_3d(p.qkv, 3LL * d, T, Bc, 3LL * d, (int64_t)T * 3 * d, 64, 256);
+    p.tm_att_o = make_tmap_3d(p.att, d, T, Bc, d, (int64_t)T * d, 64, 128);
   }
 
   // algorithmic FLOPs of one evaluation (GEMMs + attention), for roofline reporting
@@ -710,16 +719,16 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
 // =====================================================================================================
 template <int V>
 static void launch_rmsnorm(const float* x, const float* w, const float* shift, const float* scale, long long mod_ld,
-                           int rows_per_item, bf16* out, int M, float eps, cudaStream_t st) {
-  rmsnorm_mod_kernel<V><<<(M + 7) / 8, 256, 0, st>>>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps);
+                           int rows_per_item, bf16* out, int M, float eps, int reverse, cudaStream_t st) {
+  rmsnorm_mod_kernel<V><<<(M + 7) / 8, 256, 0, st>>>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps, reverse);
 }
 static void rmsnorm_mod(sab_engine* e, const float* x, const float* w, const float* shift, const float* scale,
-                        long long mod_ld, int rows_per_item, bf16* out, int M, cudaStream_t st) {
+                        long long mod_ld, int rows_per_item, bf16* out, int M, cudaStream_t st, int reverse = 0) {
   const int d = e->cfg.dim;
   const float eps = e->cfg.norm_eps;
   mark(e, st, "rmsnorm_mod", 0, (double)M * d * 6.0);
   switch (d / 128) {
-#define SAB_RN(v) case v: launch_rmsnorm<v>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps, st); break;
+#define SAB_RN(v) case v: launch_rmsnorm<v>(x, w, shift, scale, mod_ld, rows_per_item, out, M, eps, reverse, st); break;
     SAB_RN(2) SAB_RN(4) SAB_RN(8) SAB_RN(12) SAB_RN(16) SAB_RN(20) SAB_RN(22) SAB_RN(24) SAB_RN(32)
 #undef SAB_RN
     default: throw Error(fmt("rmsnorm: unsupported dim %d (add an instantiation)", d));
@@ -728,7 +737,7 @@ static void rmsnorm_mod(sab_engine* e, const float* x, const float* w, const flo
 }
 
 static void attention(sab_engine* e, const AttnParams& ap, int items, int heads, cudaStream_t st) {
-  ensure_dynamic_smem(attention_kernel, ATT_SMEM);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel), ATT_SMEM);
   const double fl = 4.0 * items * heads * (double)ap.Tq * ap.Tk * 128;
   if (ap.Tk <= XATT_MAX_TK && ap.k != ap.q) {   // a handful of text tokens: HBM-bound warp-per-row kernel
     mark(e, st, "sdpa.cross", fl, (double)items * ap.Tq * heads * 128 * 4.0);
@@ -744,7 +753,7 @@ static void attention(sab_engine* e, const AttnParams& ap, int items, int heads,
 
 static void launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& ap,
                                 int items, cudaStream_t st) {
-  ensure_dynamic_smem(attention_tc_kernel, ATC_SMEM);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel), ATC_SMEM);
   AttnTcParams p2 = ap;
   p2.items = items;
   const int n_work = ap.heads * items;
@@ -763,9 +772,48 @@ static double gemm_bytes(const GemmOp& op) {
   const double n_out = (op.mode == EPI_SWIGLU) ? P.N / 2.0 : (double)P.N;
   return op.in_bytes + op.rows * n_out * per_elem;
 }
+// second-generation tcgen05 self-attention (attention_tc2.cuh).  shift_log2 < 0 selects the exact two-pass softmax.
+static int g_attn_poly = 2;      // SAB_ATTN_POLY=0..4: pairs of every 8 whose exponential runs on the FMA pipe
+template <bool kExact, int kPoly, bool kFolded>
+static void launch_attention_tc2_inst(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                      const CUtensorMap& to, const AttnTc2Params& ap, cudaStream_t st) {
+  auto kern = attention_tc2_kernel<kExact, kPoly, kFolded>;
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), AT2_SMEM);
+  const int n_work = ap.heads * ap.items;
+  kern<<<n_work < sm_count() ? n_work : sm_count(), AT2_THREADS, AT2_SMEM, st>>>(tq, tk, tv, to, ap);
+  SAB_CUDA(cudaGetLastError());
+}
+// variants: exact (two-pass row maximum; shift_log2 < 0), single pass with scale and shift, and `folded`
+// (scale already in q, |logit| <= 50: p = 2^s) — the engine's production path
+static void launch_attention_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                                 const AttnTc2Params& ap, bool folded, cudaStream_t st) {
+  const bool exact = ap.shift_log2 < 0.f;
+  SAB_CHECK(!(exact && folded), "folded softmax needs a logit bound");
+#define SAB_AT2(p_) case p_: return exact ? launch_attention_tc2_inst<true, p_, false>(tq, tk, tv, to, ap, st)   \
+                                  : folded ? launch_attention_tc2_inst<false, p_, true>(tq, tk, tv, to, ap, st)  \
+                                           : launch_attention_tc2_inst<false, p_, false>(tq, tk, tv, to, ap, st);
+  switch (g_attn_poly) {
+    SAB_AT2(0) SAB_AT2(2) SAB_AT2(3) SAB_AT2(4)
+    default: throw Error(fmt("SAB_ATTN_POLY=%d not built (0, 2, 3, 4)", g_attn_poly));
+  }
+#undef SAB_AT2
+}
+
 static void gemm(sab_engine* e, const GemmOp& op, cudaStream_t st) {
   mark(e, st, op.tag, op.flops, gemm_bytes(op));
   launch_gemm(op, st);
+}
+// Serpentine row order.  Every kernel of a DiT layer is row-parallel and streams activations that exceed the 126 MB
+// L2 (fp32 residual 180 MB, fused QKV 270 MB, FFN hidden 241 MB at B = 64): a consumer that walks the rows in the
+// same direction as its producer finds the first rows evicted.  Alternating the direction from one launch to the
+// next makes each kernel start on the rows its producer wrote last, so roughly an L2's worth of its input (and of the
+// in-place residual it updates) never travels to HBM.
+static bool g_serpentine = true;   // SAB_NO_SERPENTINE=1 disables (A/B)
+static void gemm_dir(sab_engine* e, const GemmOp& op, int& dir, cudaStream_t st) {
+  GemmOp o2 = op;
+  o2.P.reverse_m = g_serpentine ? dir : 0;
+  dir ^= 1;
+  gemm(e, o2, st);
 }
 
 // final-layer variants: out = base + coef * velocity (ODE axpy fused in the output GEMM's epilogue)
@@ -807,28 +855,42 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
   }
   SAB_CUDA(cudaGetLastError());
   gemm(e, p.g_kvc_all, st);
+  int dir = 1;   // x_embedder.conv2 (the producer of h) walked the rows forwards
   for (int l = 0; l < NL; ++l) {
     const LayerW& W = e->layers[l];
     LayerOps& o = p.lay[l];
     const float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
-    rmsnorm_mod(e, p.h, W.attn_norm, mod_l, mod_l + d, 6LL * d, T, p.xn, M, st);
-    gemm(e, o.qkv, st);
+    rmsnorm_mod(e, p.h, W.attn_norm, mod_l, mod_l + d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
+    dir ^= 1;
+    gemm_dir(e, o.qkv, dir, st);
     AttnParams a{};
     a.q = p.qkv; a.q_ld = 3 * d; a.q_col0 = 0;
     a.k = p.qkv; a.k_ld = 3 * d; a.k_col0 = d;
     a.v = p.qkv; a.v_ld = 3 * d; a.v_col0 = 2 * d;
-    a.o = p.att; a.o_ld = d; a.key_mask = p.pad_mask; a.Tq = T; a.Tk = T; a.scale_log2 = sl2; a.mask_div = cand;
-    if (p.att_tc) {
+    a.o = p.att; a.o_ld = d; a.key_mask = p.pad_mask; a.Tq = T; a.Tk = T; a.mask_div = cand;
+    a.scale_log2 = 1.f;          // self-attention: log2(e)/sqrt(hd) is folded into q by the QKV epilogue (W.qn_scaled)
+    static const bool attn_v1 = getenv("SAB_ATTN_V1") != nullptr;   // A/B against the first-generation kernel
+    if (p.att_tc && !attn_v1) {
+      AttnTc2Params tp{};
+      tp.key_mask = p.pad_mask; tp.T = T; tp.heads = H; tp.items = Bc; tp.mask_div = cand;
+      // the softmax scale is already in q (QKV epilogue, W.qn_scaled): scale 1 for the exact fallback, and with a
+      // logit bound the folded single-pass kernel needs neither scale nor shift
+      tp.q_col0 = 0; tp.k_col0 = d; tp.v_col0 = 2 * d; tp.scale_log2 = 1.f; tp.shift_log2 = W.att_shift_log2;
+      tp.reverse = g_serpentine ? dir : 0;
+      dir ^= 1;
+      mark(e, st, "sdpa.self", 4.0 * Bc * H * (double)T * T * 128, 0);
+      launch_attention_tc2(p.tm_att_q, p.tm_att_kv, p.tm_att_kv, p.tm_att_o, tp, W.att_shift_log2 >= 0.f, st);
+    } else if (p.att_tc) {
       AttnTcParams tp{};
       tp.o = p.att; tp.o_ld = d; tp.key_mask = p.pad_mask; tp.Tq = T; tp.Tk = T; tp.heads = H; tp.mask_div = cand;
-      tp.q_col0 = 0; tp.k_col0 = d; tp.v_col0 = 2 * d; tp.scale_log2 = sl2; tp.v_lbo = ATC_KV_BYTES / 2; tp.v_sbo = 1024;
+      tp.q_col0 = 0; tp.k_col0 = d; tp.v_col0 = 2 * d; tp.scale_log2 = 1.f; tp.v_lbo = ATC_KV_BYTES / 2; tp.v_sbo = 1024;
       mark(e, st, "sdpa.self", 4.0 * Bc * H * (double)T * T * 128, 0);
       launch_attention_tc(p.tm_att_q, p.tm_att_kv, p.tm_att_kv, tp, Bc, st);
     } else {
       attention(e, a, Bc, H, st);
     }
-    gemm(e, o.wo, st);
-    gemm(e, o.q_c, st);
+    gemm_dir(e, o.wo, dir, st);
+    gemm_dir(e, o.q_c, dir, st);
     if (!p.xa_fused) {
       AttnParams x{};
       x.q = p.qc; x.q_ld = d; x.q_col0 = 0;
@@ -838,10 +900,11 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
       x.kv_div = cand; x.mask_div = cand;
       attention(e, x, Bc, H, st);
     }
-    gemm(e, o.wo_c, st);
-    rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st);
-    gemm(e, o.w13, st);
-    gemm(e, o.w2, st);
+    gemm_dir(e, o.wo_c, dir, st);
+    rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
+    dir ^= 1;
+    gemm_dir(e, o.w13, dir, st);
+    gemm_dir(e, o.w2, dir, st);
   }
   rmsnorm_mod(e, p.h, e->final_norm, p.fin, p.fin + d, 2LL * d, T, p.xn, M, st);
   GemmOp out = p.g_out;
@@ -1128,6 +1191,8 @@ int sab_create(const sab_config* cfg, int device, sab_engine** out) {
   SAB_CUDA(cudaGetDeviceProperties(&prop, device));
   SAB_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   if (const char* f = getenv("SAB_FORCE_CG")) g_force_cg = atoi(f);
+  if (const char* f = getenv("SAB_ATTN_POLY")) g_attn_poly = atoi(f);
+  g_serpentine = getenv("SAB_NO_SERPENTINE") == nullptr;
   SAB_CHECK(cfg->dim % 128 == 0 && cfg->dim / cfg->n_heads == 128, "dim must be n_heads*128");
   SAB_CHECK(cfg->ffn_hidden % 64 == 0, "ffn_hidden must be a multiple of 64");
   SAB_CHECK(cfg->codec_n_rates >= 1 && cfg->codec_n_rates <= 8, "bad codec_n_rates");
@@ -1217,6 +1282,21 @@ int sab_finalize_weights(sab_engine* e, int allow_missing, char* missing_out, in
                                                          e->cfg.anchor_dim);
   SAB_CUDA(cudaGetLastError());
   SAB_CUDA(cudaStreamSynchronize(st));
+  // self-attention logit bound per layer (see LayerW::att_shift_log2).  The single-pass softmax subtracts this
+  // constant instead of the row maximum; it is used only while even a row whose keys are all anti-aligned keeps
+  // its largest probability above 2^-100 (2 x shift <= 100), otherwise the layer runs the exact two-pass variant.
+  for (auto& W : e->layers) {
+    float qn[128], kn[128];
+    SAB_CUDA(cudaMemcpy(qn, W.qn, sizeof(qn), cudaMemcpyDeviceToHost));
+    SAB_CUDA(cudaMemcpy(kn, W.kn, sizeof(kn), cudaMemcpyDeviceToHost));
+    float mq = 0.f, mk = 0.f;
+    for (int i = 0; i < 128; ++i) { mq = fmaxf(mq, fabsf(qn[i])); mk = fmaxf(mk, fabsf(kn[i])); }
+    const float sl2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+    for (int i = 0; i < 128; ++i) qn[i] *= sl2;
+    SAB_CUDA(cudaMemcpy(W.qn_scaled, qn, sizeof(qn), cudaMemcpyHostToDevice));
+    const float bound = sqrtf(128.f) * mq * mk * 1.4426950408889634f * 1.02f + 0.25f;   // + bf16 rounding of q, k
+    W.att_shift_log2 = (std::isfinite(bound) && bound <= 50.f && !getenv("SAB_ATTN_EXACT")) ? bound : -1.f;
+  }
   e->finalized = true;
   SAB_API_END
 }
@@ -1534,7 +1614,7 @@ int sab_test_gemm(int M, int N, int K, const void* a_bf16, const void* b_bf16, f
 int sab_test_attention(int items, int heads, int Tq, int Tk, const void* q, const void* k, const void* v,
                        const uint8_t* key_mask, void* o, void* stream) {
   SAB_API_BEGIN
-  ensure_dynamic_smem(attention_kernel, ATT_SMEM);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(attention_kernel), ATT_SMEM);
   AttnParams a{};
   const long long ld = (long long)heads * 128;
   a.q = (const bf16*)q; a.q_ld = ld; a.k = (const bf16*)k; a.k_ld = ld; a.v = (const bf16*)v; a.v_ld = ld;
@@ -1565,6 +1645,35 @@ int sab_test_attention_tc(int items, int heads, int T, const void* q, const void
   tp.v_lbo = v_lbo > 0 ? v_lbo : ATC_KV_BYTES / 2;
   tp.v_sbo = v_sbo > 0 ? v_sbo : 1024;
   launch_attention_tc(tq, tk, tv, tp, items, (cudaStream_t)stream);
+  SAB_API_END
+}
+
+int sab_test_attention_tc2(int items, int heads, int T, const void* q, const void* k, const void* v,
+                           const uint8_t* key_mask, void* o, float shift_log2, int poly, long long* trace, void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(T <= 256 && T >= 1, "tcgen05 attention handles 1 <= T <= 256");
+  const long long ld = (long long)heads * 128;
+  CUtensorMap tq = make_tmap_3d(q, ld, T, items, ld, (int64_t)T * ld, 64, 128);
+  CUtensorMap tk = make_tmap_3d(k, ld, T, items, ld, (int64_t)T * ld, 64, 256);
+  CUtensorMap tv = make_tmap_3d(v, ld, T, items, ld, (int64_t)T * ld, 64, 256);
+  CUtensorMap to = make_tmap_3d(o, ld, T, items, ld, (int64_t)T * ld, 64, 128);
+  AttnTc2Params tp{};
+  tp.key_mask = key_mask; tp.T = T; tp.heads = heads; tp.items = items; tp.mask_div = 1;
+  tp.q_col0 = tp.k_col0 = tp.v_col0 = 0;
+  tp.scale_log2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+  tp.shift_log2 = shift_log2;
+  tp.trace = trace;
+  const int saved = g_attn_poly;
+  if (poly >= 0) g_attn_poly = poly;
+  try {
+    // shift_log2 == 0: folded path (the caller passes q already multiplied by log2(e)/sqrt(hd), |logit| <= 50)
+    if (shift_log2 == 0.f) tp.shift_log2 = 50.f;
+    launch_attention_tc2(tq, tk, tv, to, tp, shift_log2 == 0.f, (cudaStream_t)stream);
+  } catch (...) {
+    g_attn_poly = saved;
+    throw;
+  }
+  g_attn_poly = saved;
   SAB_API_END
 }
 

@@ -49,6 +49,7 @@ struct GemmParams {
   int N;                // valid output columns
   int n_tiles_n;
   int group_m;          // rasterisation: unit m-tiles per L2-resident A panel
+  int reverse_m;        // walk the m-tiles from the last row block to the first (see engine.cu "serpentine")
   // K loop
   int n_runs[2];
   KRun runs[2][GEMM_MAX_RUNS];
@@ -155,7 +156,7 @@ SAB_DEVICE void tmem_dealloc_cg2(uint32_t taddr) {
 }
 
 // tile -> (unit m-tile, n-tile): groups of `group_m` m-tiles sweep n (m fastest inside a group)
-SAB_DEVICE void tile_coords(int tile, int n_tiles_m, int n_tiles_n, int group_m, int& mt, int& nt) {
+SAB_DEVICE void tile_coords(int tile, int n_tiles_m, int n_tiles_n, int group_m, int reverse_m, int& mt, int& nt) {
   const int per_group = group_m * n_tiles_n;
   const int g = tile / per_group;
   const int idx = tile - g * per_group;
@@ -163,6 +164,7 @@ SAB_DEVICE void tile_coords(int tile, int n_tiles_m, int n_tiles_n, int group_m,
   const int gsz = (n_tiles_m - m_first < group_m) ? (n_tiles_m - m_first) : group_m;
   nt = idx / gsz;
   mt = m_first + (idx - nt * gsz);
+  if (reverse_m) mt = n_tiles_m - 1 - mt;
 }
 
 SAB_DEVICE uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
@@ -249,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = unit; tile < n_tiles; tile += n_units) {
         int mt, nt;
-        tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
+        tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, P.reverse_m, mt, nt);
         const int item = mt / P.tiles_per_item;
         const int t0 = (mt % P.tiles_per_item) * (GEMM_BM * CG) + (int)cta_rank * GEMM_BM;
         const int n0 = nt * BN;
@@ -304,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       for (int tile = unit; tile < n_tiles; tile += n_units) {
         int mt, nt;
-        tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
+        tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, P.reverse_m, mt, nt);
         const int n0 = nt * BN;
         const int list = (P.n_period > 0 && (n0 % P.n_period) >= P.n_switch) ? 1 : 0;
         int total_kb = 0;
@@ -356,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     for (int tile = unit; tile < n_tiles; tile += n_units) {
       int mt, nt;
-      tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, mt, nt);
+      tile_coords(tile, n_tiles_m, P.n_tiles_n, P.group_m, P.reverse_m, mt, nt);
       const int item = mt / P.tiles_per_item;
       const int t_base = (mt % P.tiles_per_item) * (GEMM_BM * CG) + (int)cta_rank * GEMM_BM + q * 32;  // row of lane 0
       const long long row0 = (long long)item * P.rows_per_item + t_base + tr_r;   // this lane's row in pass 0

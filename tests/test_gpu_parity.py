@@ -83,6 +83,49 @@ def test_tcgen05_self_attention(capi, items, heads, T):
     assert rel_l2(o.float(), ref) < 1e-2
 
 
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("items,heads,T", [(1, 1, 256), (2, 3, 250), (3, 2, 37), (2, 2, 129), (1, 1, 1), (2, 1, 128),
+                                           (40, 8, 250), (37, 5, 131)])
+def test_tcgen05_self_attention_v2(capi, items, heads, T, exact):
+    """Second-generation kernel (attention_tc2.cuh): 16 softmax warps, P/O per key half in TMEM, TMA-stored output;
+    exact = two-pass row maximum, otherwise the single-pass softmax with a logit bound (here the Cauchy-Schwarz bound
+    of the actual q, k); polynomial exp2 on 3 of 8 pairs.  The last two shapes give every persistent CTA several work
+    items (the cross-item pipeline: prefetch, TMEM hand-over, staging-tile hand-over)."""
+    g = torch.Generator(device="cuda").manual_seed(T + items)
+    q, k, v = (torch.randn(items * T, heads * 128, device="cuda", generator=g).bfloat16() for _ in range(3))
+    mask = torch.ones(items, T, dtype=torch.uint8, device="cuda")
+    for i in range(items):
+        mask[i, max(1, T - 3 * (i % 7 + 1)):] = 0
+    o = torch.full((items * T, heads * 128), float("nan"), device="cuda", dtype=torch.bfloat16)
+    qn = q.float().view(-1, heads, 128).norm(dim=-1).max()
+    kn = k.float().view(-1, heads, 128).norm(dim=-1).max()
+    shift = -1.0 if exact else float(qn * kn / 128 ** 0.5 * 1.4426950408889634) + 0.25
+    qf, kf, vf = (x.float().view(items, T, heads, 128).permute(0, 2, 1, 3) for x in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2) / 128 ** 0.5).masked_fill(~mask.bool()[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(items * T, heads * 128)
+    for poly in (3, 0):
+        o.fill_(float("nan"))
+        capi.check(capi.lib().sab_test_attention_tc2(items, heads, T, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                     mask.data_ptr(), o.data_ptr(), shift, poly, None, capi.stream_ptr()))
+        torch.cuda.synchronize()
+        assert not torch.isnan(o.float()).any()
+        assert rel_l2(o.float(), ref) < 1e-2, (poly, exact)
+    if not exact:
+        # the engine's production variant: log2(e)/sqrt(hd) already folded into q (as the QKV epilogue does), logits
+        # bounded by 50 in the log2 domain, p = 2^s with neither scale nor shift (shift_log2 == 0 selects it)
+        qs = (q.float() * (1.4426950408889634 / 128 ** 0.5)).bfloat16()
+        s2 = (qs.float().view(items, T, heads, 128).permute(0, 2, 1, 3) @ kf.transpose(-1, -2)) * 0.6931471805599453
+        assert float(s2.abs().max()) < 50 * 0.6931471805599453
+        ref2 = (torch.softmax(s2.masked_fill(~mask.bool()[:, None, None, :], float("-inf")), -1) @ vf)
+        ref2 = ref2.permute(0, 2, 1, 3).reshape(items * T, heads * 128)
+        o.fill_(float("nan"))
+        capi.check(capi.lib().sab_test_attention_tc2(items, heads, T, qs.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                     mask.data_ptr(), o.data_ptr(), 0.0, 3, None, capi.stream_ptr()))
+        torch.cuda.synchronize()
+        assert not torch.isnan(o.float()).any()
+        assert rel_l2(o.float(), ref2) < 1e-2
+
+
 def test_long_sequence_uses_streaming_attention(tiny_model):
     """T > 256 frames (a 12 s clip) falls back from the single-pass tcgen05 kernel to the streaming one;
     the result must agree with the same clip's first 10 s only in shape/finite-ness (different content),
@@ -141,6 +184,7 @@ def test_dit_evaluation_text_lengths_vs_oracle(tiny_model, tiny_cfg, tiny_sd, L)
     time = torch.tensor([0.25, 0.75])
     ref = restate.samaudio_forward(tiny_sd, tiny_cfg, noisy, feats, text, time, torch.zeros(B, 1024, T), tmask, ids, al, pad)
     out = tiny_model.forward(noisy.cuda(), feats.cuda(), text.cuda(), time.cuda(), text_mask=tmask.cuda(),
+                             masked_video_features=torch.zeros(B, 1024, T).cuda(),      # zeros, as separate() passes
                              anchor_ids=ids.cuda(), anchor_alignment=al.cuda(), audio_pad_mask=pad.cuda())
     assert rel_l2(out.cpu(), ref) < 2e-2
 
@@ -176,6 +220,7 @@ def test_dit_evaluation_production_shapes_vs_oracle(small_model_and_sd):
     time = torch.full((B,), 0.40625)
     ref = restate.samaudio_forward(sd, cfg, noisy, feats, text, time, torch.zeros(B, 1024, T), tmask, ids, al, pad)
     out = m.forward(noisy.cuda(), feats.cuda(), text.cuda(), time.cuda(), text_mask=tmask.cuda(),
+                    masked_video_features=torch.zeros(B, 1024, T).cuda(),
                     anchor_ids=ids.cuda(), anchor_alignment=al.cuda(), audio_pad_mask=pad.cuda())
     assert rel_l2(out.cpu(), ref) < 2e-2
 
