@@ -84,6 +84,31 @@ __global__ void build_mod_kernel(const float* __restrict__ tables /*[L,6,d]*/, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused RMSNorm + modulate tables for one NFE (see gemm_tc.cuh): for norm k = 2l (attention_norm of layer l, adaLN rows
+// 0/1 = shift_msa/scale_msa) or 2l+1 (ffn_norm, rows 3/4):
+//   cs[k][b][:]    = w_norm_k * (1 + scale)          (column scale the producer applies to h)
+//   shift[k][b][:] = bf16(shift)                     (A operand of the per-item bias GEMM shift @ W^T)
+// ---------------------------------------------------------------------------------------------
+__global__ void norm_tables_kernel(const float* __restrict__ mod /*[L,B,6,d]*/, const float* __restrict__ norm_w /*[2L,d]*/,
+                                   int L, int B, int d, float* __restrict__ cs /*[2L,B,d]*/,
+                                   __nv_bfloat16* __restrict__ shift /*[2L,B,d]*/) {
+  const long long n4 = (long long)2 * L * B * d / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const int c = (int)(e % d);
+    const int b = (int)((e / d) % B);
+    const int k = (int)(e / ((long long)d * B));
+    const int l = k >> 1, r0 = (k & 1) * 3;
+    const float* m = mod + (((long long)l * B + b) * 6 + r0) * d + c;
+    const float4 sh = *reinterpret_cast<const float4*>(m);
+    const float4 sc = *reinterpret_cast<const float4*>(m + d);
+    const float4 w = *reinterpret_cast<const float4*>(norm_w + (long long)k * d + c);
+    *reinterpret_cast<float4*>(cs + e) = make_float4(w.x * (1.f + sc.x), w.y * (1.f + sc.y), w.z * (1.f + sc.z), w.w * (1.f + sc.w));
+    *reinterpret_cast<uint2*>(shift + e) = make_uint2(pack_bf16(sh.x, sh.y), pack_bf16(sh.z, sh.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Timestep features (transformer.py:236-253: cat(cos,sin) of t*exp(-ln(1e4) i/128), raw t)  -> bf16 [B,256]
 // and the memory input (model.py:30-42,170-172: memory_proj(text) + cat(cos,sin)(t*exp(-ln(1e4) i/(d/2)))) -> bf16 [B*L,d]
 // ---------------------------------------------------------------------------------------------

@@ -102,6 +102,8 @@ static void launch_gemm(const GemmOp& op, cudaStream_t st) {
 #define SAB_CASE(bn_, bk_, md_, cg_) \
   if (op.BN == bn_ && op.BK == bk_ && op.mode == md_ && op.cg == cg_) return launch_gemm_inst<bn_, bk_, md_, cg_>(op, st);
   SAB_CASE(256, 64, EPI_AFFINE, 2)
+  SAB_CASE(256, 64, EPI_AFFINE_NORM, 2)
+  SAB_CASE(256, 64, EPI_AFFINE_NORM, 1)
   SAB_CASE(256, 64, EPI_SWIGLU, 2)
   SAB_CASE(256, 64, EPI_QKV, 2)
   SAB_CASE(256, 64, EPI_AFFINE, 1)
@@ -289,6 +291,7 @@ struct sab_engine {
   bf16 *xe_w[2]; float *xe_b[2], *xe_gn_w[2], *xe_gn_b[2];
   bf16 *t_w13, *t_w2, *tb_w, *y_w13, *y_w2, *w_out;
   float *tb_b, *final_norm, *final_table;
+  float* norm_w_all = nullptr;      // [2L, d]: attention_norm / ffn_norm weights of every layer, contiguous (finalize)
   float2* rope = nullptr;
   int rope_len = 0;
 
@@ -448,6 +451,7 @@ static void register_weights(sab_engine* e) {
   reg_linear(e, "transformer.output.weight", c.out_channels, d, &e->w_out);
   reg_f32(e, "transformer.final_layer_scale_shift_table", {2, d}, &e->final_table);
   // ---- DiT layers ----
+  e->norm_w_all = e->wpool.alloc<float>((int64_t)2 * L * d, true);
   e->tables = e->wpool.alloc<float>((int64_t)L * 6 * d, true);
   e->wkv_c_all = e->wpool.alloc<bf16>((int64_t)L * 2 * d * d, true);   // all layers' cross wk|wv: one GEMM per evaluation
   e->kn_c_all = e->wpool.alloc<float>((int64_t)L * 128, true);
@@ -551,12 +555,19 @@ static void register_weights(sab_engine* e) {
 // =====================================================================================================
 struct LayerOps {
   GemmOp qkv, wo, q_c, kv_c, wo_c, w13, w2;
+  GemmOp bias_qkv, bias_w13;   // fused RMSNorm: shift @ W^T per item (one small GEMM each per evaluation)
 };
 struct DitPlan {
   int B = 0, cand = 1;                  // clips and candidates per clip: Bc = B * cand sequences (candidate-minor)
   int Bc = 0, T = 0, L = 0;
   int64_t M = 0, MB = 0, ML = 0;        // sequence rows Bc*T, clip rows B*T, clip text rows B*L
   float* condB = nullptr;               // clip-level conditioning GEMM output (aliases cond when cand == 1)
+  // fused RMSNorm + modulate (gemm_tc.cuh): column scales w*(1+scale) [2NL, Bc, d], bf16 shifts [2NL, Bc, d],
+  // per-(row, n-tile, warp half) partial sums of squares [M, ssq_n], per-item biases shift @ W^T
+  bool fused_norm = false;
+  float *nrm_cs = nullptr, *nrm_ssq = nullptr, *nrm_bias_qkv = nullptr, *nrm_bias_w13 = nullptr;
+  bf16* nrm_shift = nullptr;
+  int ssq_n = 0;
   DevicePool pool;
   // activations
   float *y, *ymid, *cond, *x0, *c1, *h, *t, *t0, *mod, *fin, *mem_base, *time_dev, *vproj;
@@ -588,7 +599,7 @@ struct DitPlan {
 // the once-per-call GEMMs and the text path (memory, y_embedder, cross K/V) run on B clips and the per-sequence
 // consumers index clip = sequence / cand.  Inside sab_solve every sequence sees the same time, so the text path of
 // a clip is the same for all of its candidates; sab_dit_forward is only used with cand == 1.
-static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
+static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_ids_cap) {
   const int Bc = B * cand;
   const sab_config& c = e->cfg;
   const int d = c.dim, hid = c.ffn_hidden, NL = c.n_layers;
@@ -617,7 +628,16 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
   p.vid_bf = w.alloc<bf16>(MB * c.vision_dim);
   p.gn_partial = w.alloc<double>((int64_t)Bc * GN_CHUNKS * 2);
   p.pad_mask = w.alloc<uint8_t>(MB); p.text_mask = w.alloc<uint8_t>(ML);
-  p.n_ids_cap = 64;
+  p.fused_norm = !getenv("SAB_NO_FUSED_NORM");
+  if (p.fused_norm) {
+    p.ssq_n = 2 * ((d + 255) / 256);
+    p.nrm_cs = w.alloc<float>((int64_t)2 * NL * Bc * d);
+    p.nrm_shift = w.alloc<bf16>((int64_t)2 * NL * Bc * d);
+    p.nrm_ssq = w.alloc<float>(M * p.ssq_n, true);
+    p.nrm_bias_qkv = w.alloc<float>((int64_t)NL * Bc * 3 * d);
+    p.nrm_bias_w13 = w.alloc<float>((int64_t)NL * Bc * 2 * hid);
+  }
+  p.n_ids_cap = n_ids_cap;
   p.anchor_ids = w.alloc<long long>((int64_t)B * p.n_ids_cap); p.anchor_align = w.alloc<long long>(MB);
 
   // ---- once-per-call conditioning GEMMs ----
@@ -650,6 +670,21 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
     p.g_xe[b].P.out_f32 = b == 0 ? p.c1 : p.h; p.g_xe[b].P.out_f32_ld = d;
     if (b == 1) { p.g_xe[b].P.res = p.x0; p.g_xe[b].P.res_ld = d; }
   }
+  // fused RMSNorm: the kernel that last writes h before a norm also emits that norm's GEMM operand h*w*(1+scale) (into
+  // xn) and the partial sums of squares; `which` = 2l (attention_norm of layer l) or 2l+1 (ffn_norm)
+  auto norm_producer = [&](GemmOp& op, int which) {
+    if (!p.fused_norm) return;
+    op.mode = EPI_AFFINE_NORM;
+    op.P.colscale = p.nrm_cs + (int64_t)which * Bc * d; op.P.colscale_ld = d; op.P.gate_div = T;
+    op.P.out_scaled = p.xn; op.P.out_scaled_ld = d;
+    op.P.ssq_out = p.nrm_ssq; op.P.ssq_ld = p.ssq_n;
+  };
+  auto norm_consumer = [&](GemmOp& op, const float* bias, long long bias_ld) {
+    if (!p.fused_norm) return;
+    op.P.ssq_in = p.nrm_ssq; op.P.ssq_n = p.ssq_n; op.P.ssq_inv_dim = 1.0f / (float)d;
+    op.P.ibias = bias; op.P.ibias_ld = bias_ld; op.P.ibias_div = T;
+  };
+  norm_producer(p.g_xe[1], 0);
   // ---- layers ----
   p.lay.resize(NL);
   p.xa_fused = (L <= XA_MAX_TK) && !getenv("SAB_NO_FUSED_XATTN");
@@ -663,6 +698,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
     o.qkv.P.out_bf16 = p.qkv; o.qkv.P.out_bf16_ld = 3 * d;
     o.qkv.P.qnorm_w = W.qn_scaled; o.qkv.P.knorm_w = W.kn; o.qkv.P.n_q_end = d; o.qkv.P.n_k_end = 2 * d;
     o.qkv.P.rope = e->rope; o.qkv.P.rope_T = T; o.qkv.P.use_rope = 1; o.qkv.P.eps = c.norm_eps;
+    norm_consumer(o.qkv, p.nrm_bias_qkv ? p.nrm_bias_qkv + (int64_t)l * Bc * 3 * d : nullptr, 3LL * d);
     o.wo = make_linear("attention.wo", p.att, M, d, W.wo, d, 256, EPI_AFFINE);
     o.wo.P.gate = mod_l + 2 * d; o.wo.P.gate_ld = 6 * d; o.wo.P.gate_div = T;
     o.wo.P.res = p.h; o.wo.P.res_ld = d; o.wo.P.out_f32 = p.h; o.wo.P.out_f32_ld = d;
@@ -684,11 +720,23 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L) {
 
     o.wo_c = make_linear("cross.wo", p.att, M, d, W.wo_c, d, 256, EPI_AFFINE);
     o.wo_c.P.res = p.h; o.wo_c.P.res_ld = d; o.wo_c.P.out_f32 = p.h; o.wo_c.P.out_f32_ld = d;
+    norm_producer(o.wo_c, 2 * l + 1);
     o.w13 = make_linear("ffn.w13", p.xn, M, d, W.w13, 2 * hid, 256, EPI_SWIGLU);
-    o.w13.P.out_bf16 = p.u; o.w13.P.out_bf16_ld = hid;
+    o.w13.P.out_bf16 = p.u; o.w13.P.out_bf16_ld = hid; o.w13.P.eps = c.norm_eps;
+    norm_consumer(o.w13, p.nrm_bias_w13 ? p.nrm_bias_w13 + (int64_t)l * Bc * 2 * hid : nullptr, 2LL * hid);
     o.w2 = make_linear("ffn.w2", p.u, M, hid, W.w2, d, 256, EPI_AFFINE);
     o.w2.P.gate = mod_l + 5 * d; o.w2.P.gate_ld = 6 * d; o.w2.P.gate_div = T;
     o.w2.P.res = p.h; o.w2.P.res_ld = d; o.w2.P.out_f32 = p.h; o.w2.P.out_f32_ld = d;
+    if (l + 1 < NL) norm_producer(o.w2, 2 * (l + 1));      // the last layer feeds the final norm (standalone kernel)
+    if (p.fused_norm) {
+      // shift @ W^T: [Bc, d] x [N, d]^T with the SAME packed weights as the main GEMM (so the bias columns line up
+      // with its accumulator columns, head permutation and gate/up interleave included).  Weight-streaming (HBM) bound
+      // at M = Bc rows: 64-column tiles so that every SM pulls a share of the weight
+      o.bias_qkv = make_linear("norm.bias.qkv", p.nrm_shift + (int64_t)(2 * l) * Bc * d, Bc, d, W.wqkv, 3 * d, 64, EPI_AFFINE);
+      o.bias_qkv.P.out_f32 = p.nrm_bias_qkv + (int64_t)l * Bc * 3 * d; o.bias_qkv.P.out_f32_ld = 3 * d;
+      o.bias_w13 = make_linear("norm.bias.w13", p.nrm_shift + (int64_t)(2 * l + 1) * Bc * d, Bc, d, W.w13, 2 * hid, 64, EPI_AFFINE);
+      o.bias_w13.P.out_f32 = p.nrm_bias_w13 + (int64_t)l * Bc * 2 * hid; o.bias_w13.P.out_f32_ld = 2 * hid;
+    }
   }
   p.g_out = make_linear("output", p.xn, M, d, e->w_out, c.out_channels, 256, EPI_AFFINE);
   // every layer's text K|V in one GEMM per evaluation: [Bc*L, d] x [NL*2d, d]^T, k-norm per layer
@@ -840,6 +888,14 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
   gemm(e, p.g_tb, st);
   mark(e, st, "build_mod_kernel");
   build_mod_kernel<<<512, 256, 0, st>>>(e->tables, p.t0, p.mod, NL, Bc, d, e->final_table, p.t, p.fin);
+  if (p.fused_norm) {
+    mark(e, st, "norm_tables_kernel");
+    norm_tables_kernel<<<512, 256, 0, st>>>(p.mod, e->norm_w_all, NL, Bc, d, p.nrm_cs, p.nrm_shift);
+    for (int l = 0; l < NL; ++l) {
+      gemm(e, p.lay[l].bias_qkv, st);
+      gemm(e, p.lay[l].bias_w13, st);
+    }
+  }
   gemm(e, p.g_y13, st);
   gemm(e, p.g_y2, st);
   gemm(e, p.g_in, st);
@@ -860,8 +916,10 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
     const LayerW& W = e->layers[l];
     LayerOps& o = p.lay[l];
     const float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
-    rmsnorm_mod(e, p.h, W.attn_norm, mod_l, mod_l + d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
-    dir ^= 1;
+    if (!p.fused_norm) {
+      rmsnorm_mod(e, p.h, W.attn_norm, mod_l, mod_l + d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
+      dir ^= 1;
+    }
     gemm_dir(e, o.qkv, dir, st);
     AttnParams a{};
     a.q = p.qkv; a.q_ld = 3 * d; a.q_col0 = 0;
@@ -878,7 +936,7 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
       tp.q_col0 = 0; tp.k_col0 = d; tp.v_col0 = 2 * d; tp.scale_log2 = 1.f; tp.shift_log2 = W.att_shift_log2;
       tp.reverse = g_serpentine ? dir : 0;
       dir ^= 1;
-      mark(e, st, "sdpa.self", 4.0 * Bc * H * (double)T * T * 128, 0);
+      mark(e, st, "sdpa.self", 4.0 * Bc * H * (double)T * T * 128, (double)M * 4.0 * d * 2.0);   // reads q|k|v, writes o (bf16)
       launch_attention_tc2(p.tm_att_q, p.tm_att_kv, p.tm_att_kv, p.tm_att_o, tp, W.att_shift_log2 >= 0.f, st);
     } else if (p.att_tc) {
       AttnTcParams tp{};
@@ -901,8 +959,10 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
       attention(e, x, Bc, H, st);
     }
     gemm_dir(e, o.wo_c, dir, st);
-    rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
-    dir ^= 1;
+    if (!p.fused_norm) {
+      rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
+      dir ^= 1;
+    }
     gemm_dir(e, o.w13, dir, st);
     gemm_dir(e, o.w2, dir, st);
   }
@@ -1282,6 +1342,11 @@ int sab_finalize_weights(sab_engine* e, int allow_missing, char* missing_out, in
                                                          e->cfg.anchor_dim);
   SAB_CUDA(cudaGetLastError());
   SAB_CUDA(cudaStreamSynchronize(st));
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    SAB_CUDA(cudaMemcpyAsync(e->norm_w_all + (2 * l) * d, e->layers[l].attn_norm, d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SAB_CUDA(cudaMemcpyAsync(e->norm_w_all + (2 * l + 1) * d, e->layers[l].ffn_norm, d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  SAB_CUDA(cudaStreamSynchronize(st));
   // self-attention logit bound per layer (see LayerW::att_shift_log2).  The single-pass softmax subtracts this
   // constant instead of the row maximum; it is used only while even a row whose keys are all anti-aligned keeps
   // its largest probability above 2^-100 (2 x shift <= 100), otherwise the layer runs the exact two-pass variant.
@@ -1312,10 +1377,11 @@ int sab_prepare(sab_engine* e, int B, int candidates, int T, int L, const float*
   SAB_CHECK(no_text ? L == 1 : text_features != nullptr, "text_features missing (or SAB_PREP_NO_TEXT with L != 1)");
   SAB_CHECK(no_anchor || (anchor_ids && anchor_alignment && n_ids > 0), "anchor tensors missing");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!e->dit || e->dit->B != B || e->dit->cand != candidates || e->dit->T != T || e->dit->L != L) {
+  if (!e->dit || e->dit->B != B || e->dit->cand != candidates || e->dit->T != T || e->dit->L != L ||
+      n_ids > e->dit->n_ids_cap) {
     SAB_CUDA(cudaStreamSynchronize(st));
     e->dit.reset();
-    build_dit_plan(e, B, candidates, T, L);
+    build_dit_plan(e, B, candidates, T, L, std::max(64, n_ids));   // the anchor-id table grows with the longest id list
   }
   DitPlan& p = *e->dit;
   const sab_config& c = e->cfg;

@@ -33,7 +33,9 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 384;   // 4 role warps + 8 epilogue warps
 constexpr int GEMM_MAX_RUNS = 8;
 
-enum EpiMode { EPI_AFFINE = 0, EPI_SWIGLU = 1, EPI_QKV = 2 };
+// EPI_AFFINE_NORM = EPI_AFFINE + the producer half of the fused RMSNorm (own instantiation: the extra per-lane state
+// would spill in the plain affine epilogue, which is already at the 168-register cap of a 384-thread CTA)
+enum EpiMode { EPI_AFFINE = 0, EPI_SWIGLU = 1, EPI_QKV = 2, EPI_AFFINE_NORM = 3 };
 
 struct KRun {
   int row_shift;  // added to the tile's first row (rows outside [0, rows_per_item) read as zero)
@@ -63,6 +65,18 @@ struct GemmParams {
   float* out_f32; long long out_f32_ld;
   __nv_bfloat16* out_bf16; long long out_bf16_ld;
   __nv_bfloat16* out_act; long long out_act_ld; const float* snake_alpha;  // snake_alpha[n % bias_mod]
+  // fused RMSNorm + adaLN modulate (transformer.py:42-47,21-22), split between the producer of the residual stream and
+  // the GEMM that consumes the normalised rows:  norm(h)*w*(1+scale)+shift  @ W^T
+  //     =  rstd[row] * ((h * w*(1+scale)) @ W^T)  +  shift @ W^T
+  //  producer (affine epilogue): out_scaled = bf16(v * colscale[row / gate_div][n]) is the consumer's A operand and
+  //    ssq_out[row, 2*n_tile + warp_half] = sum of v^2 over the columns this epilogue warp owns (no atomics);
+  //  consumer (every mode): acc' = rstd[row] * acc + ibias[row / ibias_div][n] before anything else,
+  //    rstd[row] = rsqrt(sum_j ssq_in[row, j] * ssq_inv_dim + eps),  ibias = shift @ W^T (one small GEMM per evaluation)
+  const float* colscale; long long colscale_ld;      // item = row / gate_div (as for the adaLN gate)
+  __nv_bfloat16* out_scaled; long long out_scaled_ld;
+  float* ssq_out; int ssq_ld;
+  const float* ssq_in; int ssq_n; float ssq_inv_dim;
+  const float* ibias; long long ibias_ld; int ibias_div;
   // back-to-back mode: acc1 = Snake_{b2b_alpha}(acc0 + b2b_bias) @ W1^T, then the affine epilogue runs on acc1
   const float* b2b_bias; const float* b2b_alpha;
   // qkv epilogue
@@ -366,6 +380,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BN;
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
 
+      // fused-RMSNorm consumer: rstd and the per-item bias row of THIS LANE'S row (thread == row form); the loads are
+      // issued before the accumulator wait
+      float nrm_rstd = 1.f;
+      const float* nrm_brow = nullptr;
+      if (P.ssq_in != nullptr) {
+        const int t_thr = t_base + lane;
+        const long long grow = (long long)item * P.rows_per_item + (t_thr < P.rows_per_item ? t_thr : P.rows_per_item - 1);
+        const float* sp = P.ssq_in + grow * P.ssq_n;
+        float ssum = 0.f;
+        for (int jj = 0; jj < P.ssq_n; ++jj) ssum += __ldg(sp + jj);
+        nrm_rstd = rsqrtf(ssum * P.ssq_inv_dim + P.eps);
+        nrm_brow = P.ibias + (long long)((uint32_t)grow / (uint32_t)P.ibias_div) * P.ibias_ld + n0;
+      }
+
       // write this thread's 32 accumulator values (one row) into the staging tile, then read them back transposed
       auto stage_put = [&](const float (&v)[32]) {
         const uint32_t dst = stg + (uint32_t)(lane * kLd * 4);
@@ -378,7 +406,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int p = 0; p < 8; ++p) x[p] = lds128(stg + (uint32_t)(((4 * p + tr_r) * kLd + tr_c) * 4));
       };
 
-      if constexpr (MODE == EPI_AFFINE) {
+      constexpr bool kNorm = (MODE == EPI_AFFINE_NORM);
+      if constexpr (MODE == EPI_AFFINE || MODE == EPI_AFFINE_NORM) {
         // fp32 residual rows are fetched one chunk ahead (8 independent 16 B loads per lane in flight while the
         // previous chunk is transposed and stored); the first chunk's loads go out before the accumulator wait.
         const float* res0 = P.res ? P.res + row0 * P.res_ld + n0 + tr_c : nullptr;
@@ -391,11 +420,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (res0 && 4 * p < rl && n0 + c < P.N) r4[p] = ldg_stream128(res0 + p * res_step + c);
           }
         };
-        int goff[8];                            // adaLN gate row of each pass (one integer division per tile, not per chunk)
-        if (P.gate) {
+        // item (= row / gate_div) of each pass: indexes the adaLN gate rows and the fused-RMSNorm column-scale rows
+        // (one integer division per pass and tile, not per chunk)
+        int item_p[8];
+        if (!B2B && (P.gate || (kNorm && P.out_scaled))) {
 #pragma unroll
           for (int p = 0; p < 8; ++p)
-            goff[p] = (4 * p < rl) ? ((int)(row0 + 4 * p) / P.gate_div) * P.gate_ld : 0;
+            item_p[p] = (4 * p < rl) ? (int)((uint32_t)(row0 + 4 * p) / (uint32_t)P.gate_div) : 0;
+        }
+        float ssq[8];   // fused RMSNorm, producer side: running sum of squares of this warp's columns, per pass
+        if constexpr (kNorm) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) ssq[p] = 0.f;
         }
         if constexpr (B2B) {
           // ---- first epilogue: Snake(acc0 + bias) -> bf16 -> the K-major swizzled A tile of the second GEMM ----
@@ -446,10 +482,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (c + 64 < BN) load_res(c + 64, rr_n);
           const int n = n0 + c + tr_c;
           float4 g4[8];                         // gate values: requested before the TMEM read / transpose, used after
-          if (!B2B && P.gate) {                 // (the codec's back-to-back tiles have no gate: keep their registers)
+          if (!B2B && !kNorm && P.gate) {       // (the codec's back-to-back tiles have no gate: keep their registers)
             const float* g0 = P.gate + n;
 #pragma unroll
-            for (int p = 0; p < 8; ++p) g4[p] = __ldg(reinterpret_cast<const float4*>(g0 + goff[p]));
+            for (int p = 0; p < 8; ++p) g4[p] = __ldg(reinterpret_cast<const float4*>(g0 + item_p[p] * P.gate_ld));
           }
           float v[32];
           tmem_ld32(t_addr + c, v);
@@ -462,9 +498,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int p = 0; p < 8; ++p) { x[p].x += b4.x; x[p].y += b4.y; x[p].z += b4.z; x[p].w += b4.w; }
           }
-          if (!B2B && P.gate) {
+          if (!B2B && !kNorm && P.gate) {
 #pragma unroll
             for (int p = 0; p < 8; ++p) { x[p].x *= g4[p].x; x[p].y *= g4[p].y; x[p].z *= g4[p].z; x[p].w *= g4[p].w; }
+          }
+          if (kNorm && P.gate) {                // norm-producer instantiation: gate rows fetched at their use (L1/L2 hits)
+            const float* g0 = P.gate + n;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(g0 + item_p[p] * P.gate_ld));
+              x[p].x *= g.x; x[p].y *= g.y; x[p].z *= g.z; x[p].w *= g.w;
+            }
           }
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
@@ -491,6 +535,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int p = 0; p < 8; ++p)
               if (4 * p < rl) *reinterpret_cast<uint2*>(o0 + p * st) = pack4_bf16(x[p]);
           }
+          if (kNorm && P.out_scaled) {   // the next GEMM's A operand: h * w_norm * (1 + scale); and sum h^2
+            __nv_bfloat16* o0 = P.out_scaled + row0 * P.out_scaled_ld + n;
+            const long long st = 4 * P.out_scaled_ld;
+            const float* c0 = P.colscale + n;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(c0 + item_p[p] * P.colscale_ld));
+              ssq[p] = fmaf(x[p].x, x[p].x, fmaf(x[p].y, x[p].y, fmaf(x[p].z, x[p].z, fmaf(x[p].w, x[p].w, ssq[p]))));
+              if (4 * p < rl)
+                *reinterpret_cast<uint2*>(o0 + p * st) =
+                    pack4_bf16(make_float4(x[p].x * c4.x, x[p].y * c4.y, x[p].z * c4.z, x[p].w * c4.w));
+            }
+          }
           if (P.out_act) {   // Snake: v + sin^2(a v) / (a + 1e-9)
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.snake_alpha + (P.bias_mod ? (n % P.bias_mod) : n)));
             const float4 i4 = make_float4(rcp_approx(a4.x + 1e-9f), rcp_approx(a4.y + 1e-9f), rcp_approx(a4.z + 1e-9f), rcp_approx(a4.w + 1e-9f));
@@ -512,6 +569,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int p = 0; p < 8; ++p) rr[p] = rr_n[p];
           __syncwarp();  // staging tile is rewritten by the next chunk
         }
+        if (kNorm && P.ssq_out) {   // the 8 lanes of a row hold 4 columns each: one partial per (row, n-tile, warp half)
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            float sv = ssq[p];
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+            if ((lane & 7) == 0 && 4 * p < rl) P.ssq_out[(row0 + 4 * p) * P.ssq_ld + nt * 2 + half] = sv;
+          }
+        }
       } else if constexpr (MODE == EPI_SWIGLU) {
         // tile columns: [32 gate | 32 up] pairs -> BN/2 outputs at column n0/2; this warp owns alternating pairs
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -523,6 +590,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(t_addr + c, g);
           tmem_ld32(t_addr + c + 32, u);
           tmem_ld_wait();
+          if (P.ssq_in) {   // fused RMSNorm: rstd * acc + (shift @ W^T) of this row's item (L1-broadcast loads)
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(nrm_brow + c + j));
+              const float4 bu = __ldg(reinterpret_cast<const float4*>(nrm_brow + c + 32 + j));
+              g[j] = fmaf(g[j], nrm_rstd, bg.x); g[j + 1] = fmaf(g[j + 1], nrm_rstd, bg.y);
+              g[j + 2] = fmaf(g[j + 2], nrm_rstd, bg.z); g[j + 3] = fmaf(g[j + 3], nrm_rstd, bg.w);
+              u[j] = fmaf(u[j], nrm_rstd, bu.x); u[j + 1] = fmaf(u[j + 1], nrm_rstd, bu.y);
+              u[j + 2] = fmaf(u[j + 2], nrm_rstd, bu.z); u[j + 3] = fmaf(u[j + 3], nrm_rstd, bu.w);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) g[j] = silu_f(g[j]) * u[j];
           stage_put(g);
@@ -654,6 +732,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float v[32];
               tmem_ld32(t_addr + hc + c, v);
               tmem_ld_wait();
+              if (P.ssq_in) {   // fused RMSNorm of the GEMM's input rows: the head's values are rstd * acc + bias
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(nrm_brow + hc + c + j));
+                  v[j] = fmaf(v[j], nrm_rstd, b4.x); v[j + 1] = fmaf(v[j + 1], nrm_rstd, b4.y);
+                  v[j + 2] = fmaf(v[j + 2], nrm_rstd, b4.z); v[j + 3] = fmaf(v[j + 3], nrm_rstd, b4.w);
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
             }
@@ -662,6 +748,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float rs[8];
 #pragma unroll
           for (int p = 0; p < 8; ++p) rs[p] = __shfl_sync(0xffffffffu, rstd, 4 * p + tr_r);
+          float nrs[8];       // fused RMSNorm: rstd of each pass's row, and its item's bias row
+          int nboff[8];
+          if (P.ssq_in) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              nrs[p] = __shfl_sync(0xffffffffu, nrm_rstd, 4 * p + tr_r);
+              nboff[p] = (4 * p < rl) ? (int)((uint32_t)(row0 + 4 * p) / (uint32_t)P.ibias_div) * (int)P.ibias_ld : 0;
+            }
+          }
 #pragma unroll 1
           for (int c = (BN >= 256 ? 0 : half * 32); c < 128; c += (BN >= 256 ? 32 : 64)) {
             float v[32];
@@ -671,6 +766,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int cc = c + tr_c;              // column inside the head
             float4 x[8];
             stage_get(x);
+            if (P.ssq_in) {
+              const float* b0 = P.ibias + nh + cc;
+#pragma unroll
+              for (int p = 0; p < 8; ++p) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(b0 + nboff[p]));
+                x[p].x = fmaf(x[p].x, nrs[p], b4.x); x[p].y = fmaf(x[p].y, nrs[p], b4.y);
+                x[p].z = fmaf(x[p].z, nrs[p], b4.z); x[p].w = fmaf(x[p].w, nrs[p], b4.w);
+              }
+            }
             if (nw) {
               const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + cc));
 #pragma unroll
