@@ -112,30 +112,29 @@ __global__ void norm_tables_kernel(const float* __restrict__ mod /*[L,B,6,d]*/, 
 // Timestep features (transformer.py:236-253: cat(cos,sin) of t*exp(-ln(1e4) i/128), raw t)  -> bf16 [B,256]
 // and the memory input (model.py:30-42,170-172: memory_proj(text) + cat(cos,sin)(t*exp(-ln(1e4) i/(d/2)))) -> bf16 [B*L,d]
 // ---------------------------------------------------------------------------------------------
-__global__ void time_features_kernel(const float* __restrict__ time /*[B*cand]*/, int B /*sequences*/, int cand, int d, int L,
-                                     __nv_bfloat16* __restrict__ tfreq /*[B,256]*/,
-                                     const float* __restrict__ mem_base /*[B/cand*L,d]*/,
-                                     __nv_bfloat16* __restrict__ mem_in /*[B/cand*L,d]*/) {
-  // the text memory is per clip: its time is that of the clip's first candidate (all equal inside a solve)
-  const long long n1 = (long long)B * 256, n2 = (long long)(B / cand) * L * d;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n1 + n2;
-       i += (long long)gridDim.x * blockDim.x) {
-    if (i < n1) {
-      const int b = (int)(i / 256), c = (int)(i % 256);
-      const int k = c & 127;
-      const float f = expf(-logf(10000.f) * (float)k / 128.f);
-      const float a = time[b] * f;
-      tfreq[i] = __float2bfloat16(c < 128 ? cosf(a) : sinf(a));
-    } else {
-      const long long e = i - n1;
-      const int c = (int)(e % d);
-      const int b = (int)(e / ((long long)L * d));
-      const int half = d / 2;
-      const int k = c < half ? c : c - half;
-      const float f = expf(-logf(10000.f) * (float)k / (float)half);
-      const float a = time[(long long)b * cand] * f;
-      mem_in[e] = __float2bfloat16(mem_base[e] + (c < half ? cosf(a) : sinf(a)));
-    }
+__global__ void tfreq_kernel(const float* __restrict__ time /*[R]*/, int R, __nv_bfloat16* __restrict__ tfreq /*[R,256]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 256) return;
+  const int b = i / 256, c = i % 256;
+  const int k = c & 127;
+  const float f = expf(-logf(10000.f) * (float)k / 128.f);
+  const float a = time[b] * f;
+  tfreq[i] = __float2bfloat16(c < 128 ? cosf(a) : sinf(a));
+}
+// text memory input: memory_proj(text) + cat(cos, sin)(t * exp(-ln(1e4) i/(d/2))) per CLIP; its time is that of the
+// clip's first candidate (all equal inside a solve)
+__global__ void mem_time_kernel(const float* __restrict__ time /*[B*cand]*/, int B /*sequences*/, int cand, int d, int L,
+                                const float* __restrict__ mem_base /*[B/cand*L,d]*/,
+                                __nv_bfloat16* __restrict__ mem_in /*[B/cand*L,d]*/) {
+  const long long n2 = (long long)(B / cand) * L * d;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n2; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d);
+    const int b = (int)(e / ((long long)L * d));
+    const int half = d / 2;
+    const int k = c < half ? c : c - half;
+    const float f = expf(-logf(10000.f) * (float)k / (float)half);
+    const float a = time[(long long)b * cand] * f;
+    mem_in[e] = __float2bfloat16(mem_base[e] + (c < half ? cosf(a) : sinf(a)));
   }
 }
 

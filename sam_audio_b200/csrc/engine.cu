@@ -555,8 +555,23 @@ static void register_weights(sab_engine* e) {
 // =====================================================================================================
 struct LayerOps {
   GemmOp qkv, wo, q_c, kv_c, wo_c, w13, w2;
-  GemmOp bias_qkv, bias_w13;   // fused RMSNorm: shift @ W^T per item (one small GEMM each per evaluation)
 };
+// Everything of a DiT evaluation that depends on the evaluation TIME only (transformer.py:482-493, 363-371, 507-509):
+// the timestep embedding, t_block, the adaLN tables of every layer, and — for the fused RMSNorm — the column scales
+// w*(1+scale) and the biases shift @ W^T.  R rows = one per sequence (sab_dit_forward: every sequence has its own time)
+// or one per evaluation of a solve (sab_solve: all sequences share the time, so the 2*n_steps rows are computed ONCE
+// per plan instead of inside the ODE loop, and every consumer reads row k with an item stride of 0).
+struct TimeState {
+  int R = 0;
+  float *time = nullptr, *t = nullptr, *t0 = nullptr, *mod = nullptr, *fin = nullptr, *cs = nullptr;
+  float *bias_qkv = nullptr, *bias_w13 = nullptr;
+  bf16 *tfreq = nullptr, *t_h = nullptr, *t_silu = nullptr, *shift = nullptr;
+  GemmOp g_t13, g_t2, g_tb;
+  std::vector<GemmOp> g_bias_qkv, g_bias_w13;
+  bool valid = false;      // hoisted state: tables match the current weights and step count
+  int n_steps = 0;
+};
+
 struct DitPlan {
   int B = 0, cand = 1;                  // clips and candidates per clip: Bc = B * cand sequences (candidate-minor)
   int Bc = 0, T = 0, L = 0;
@@ -565,20 +580,20 @@ struct DitPlan {
   // fused RMSNorm + modulate (gemm_tc.cuh): column scales w*(1+scale) [2NL, Bc, d], bf16 shifts [2NL, Bc, d],
   // per-(row, n-tile, warp half) partial sums of squares [M, ssq_n], per-item biases shift @ W^T
   bool fused_norm = false;
-  float *nrm_cs = nullptr, *nrm_ssq = nullptr, *nrm_bias_qkv = nullptr, *nrm_bias_w13 = nullptr;
-  bf16* nrm_shift = nullptr;
+  float* nrm_ssq = nullptr;
   int ssq_n = 0;
+  TimeState ts_item;     // per-sequence times (sab_dit_forward), recomputed every evaluation
+  TimeState ts_solve;    // one row per evaluation of the ODE grid (sab_solve), computed once
   DevicePool pool;
   // activations
-  float *y, *ymid, *cond, *x0, *c1, *h, *t, *t0, *mod, *fin, *mem_base, *time_dev, *vproj;
-  bf16 *y_bf, *gn_a, *hb, *xn, *qkv, *att, *qc, *kvc, *u, *tfreq, *t_h, *t_silu, *mem_in, *y_h, *ymem, *feat_bf,
-      *text_bf, *vid_bf;
+  float *y, *ymid, *cond, *x0, *c1, *h, *mem_base, *time_dev, *vproj;
+  bf16 *y_bf, *gn_a, *hb, *xn, *qkv, *att, *qc, *kvc, *u, *mem_in, *y_h, *ymem, *feat_bf, *text_bf, *vid_bf;
   double* gn_partial;
   uint8_t *pad_mask, *text_mask;
   long long *anchor_ids, *anchor_align;
   int n_ids_cap = 0;
   // ops
-  GemmOp g_t13, g_t2, g_tb, g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid, g_kvc_all;
+  GemmOp g_y13, g_y2, g_in, g_xe[2], g_out, g_cond, g_mem, g_vid, g_kvc_all;
   std::vector<LayerOps> lay;
   CUtensorMap tm_att_q, tm_att_kv;   // fused-QKV buffer viewed as (3d cols, T rows, Bc items): box 64x128 / 64x256
   CUtensorMap tm_att_o;              // attention output viewed as (d cols, T rows, Bc items): box 64x128 (TMA store)
@@ -594,6 +609,42 @@ struct DitPlan {
   int time_steps_uploaded = 0;
   ~DitPlan() { if (solve_graph) cudaGraphExecDestroy(solve_graph); }
 };
+
+static void build_time_state(sab_engine* e, DitPlan& p, TimeState& ts, int R) {
+  const sab_config& c = e->cfg;
+  const int d = c.dim, hid = c.ffn_hidden, NL = c.n_layers;
+  DevicePool& w = p.pool;
+  ts.R = R;
+  ts.time = w.alloc<float>(R);
+  ts.t = w.alloc<float>((int64_t)R * d); ts.t0 = w.alloc<float>((int64_t)R * 6 * d);
+  ts.mod = w.alloc<float>((int64_t)NL * R * 6 * d); ts.fin = w.alloc<float>((int64_t)R * 2 * d);
+  ts.tfreq = w.alloc<bf16>((int64_t)R * 256); ts.t_h = w.alloc<bf16>((int64_t)R * d);
+  ts.t_silu = w.alloc<bf16>((int64_t)R * d);
+  ts.g_t13 = make_linear("t_embedder.w13", ts.tfreq, R, 256, e->t_w13, 2 * d, 256, EPI_SWIGLU);
+  ts.g_t13.P.out_bf16 = ts.t_h; ts.g_t13.P.out_bf16_ld = d;
+  ts.g_t2 = make_linear("t_embedder.w2", ts.t_h, R, d, e->t_w2, d, 256, EPI_AFFINE);
+  ts.g_t2.P.out_f32 = ts.t; ts.g_t2.P.out_f32_ld = d;
+  ts.g_tb = make_linear("t_block", ts.t_silu, R, d, e->tb_w, 6 * d, 256, EPI_AFFINE);
+  ts.g_tb.P.bias = e->tb_b; ts.g_tb.P.out_f32 = ts.t0; ts.g_tb.P.out_f32_ld = 6 * d;
+  if (p.fused_norm) {
+    ts.cs = w.alloc<float>((int64_t)2 * NL * R * d);
+    ts.shift = w.alloc<bf16>((int64_t)2 * NL * R * d);
+    ts.bias_qkv = w.alloc<float>((int64_t)NL * R * 3 * d);
+    ts.bias_w13 = w.alloc<float>((int64_t)NL * R * 2 * hid);
+    ts.g_bias_qkv.resize(NL);
+    ts.g_bias_w13.resize(NL);
+    for (int l = 0; l < NL; ++l) {
+      const LayerW& W = e->layers[l];
+      // shift @ W^T: [R, d] x [N, d]^T with the SAME packed weights as the main GEMM (so the bias columns line up
+      // with its accumulator columns, head permutation and gate/up interleave included).  Weight-streaming (HBM) bound
+      // at a handful of rows: 64-column tiles so that every SM pulls a share of the weight
+      ts.g_bias_qkv[l] = make_linear("norm.bias.qkv", ts.shift + (int64_t)(2 * l) * R * d, R, d, W.wqkv, 3 * d, 64, EPI_AFFINE);
+      ts.g_bias_qkv[l].P.out_f32 = ts.bias_qkv + (int64_t)l * R * 3 * d; ts.g_bias_qkv[l].P.out_f32_ld = 3 * d;
+      ts.g_bias_w13[l] = make_linear("norm.bias.w13", ts.shift + (int64_t)(2 * l + 1) * R * d, R, d, W.w13, 2 * hid, 64, EPI_AFFINE);
+      ts.g_bias_w13[l].P.out_f32 = ts.bias_w13 + (int64_t)l * R * 2 * hid; ts.g_bias_w13[l].P.out_f32_ld = 2 * hid;
+    }
+  }
+}
 
 // Conditioning (features, text, video, anchors, masks) is per CLIP; the candidates of a clip (model.py:193-203) share it:
 // the once-per-call GEMMs and the text path (memory, y_embedder, cross K/V) run on B clips and the per-sequence
@@ -614,15 +665,11 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   p.cond = w.alloc<float>(M * d); p.x0 = w.alloc<float>(M * d); p.c1 = w.alloc<float>(M * d);
   p.h = w.alloc<float>(M * d); p.vproj = w.alloc<float>(MB * d);
   p.condB = cand == 1 ? p.cond : w.alloc<float>(MB * d);
-  p.t = w.alloc<float>((int64_t)Bc * d); p.t0 = w.alloc<float>((int64_t)Bc * 6 * d);
-  p.mod = w.alloc<float>((int64_t)NL * Bc * 6 * d); p.fin = w.alloc<float>((int64_t)Bc * 2 * d);
   p.mem_base = w.alloc<float>(ML * d);
   p.time_dev = w.alloc<float>((int64_t)Bc * 64);
   p.y_bf = w.alloc<bf16>(M * 256); p.gn_a = w.alloc<bf16>(M * d); p.hb = w.alloc<bf16>(M * d);
   p.xn = w.alloc<bf16>(M * d); p.qkv = w.alloc<bf16>(M * 3 * d); p.att = w.alloc<bf16>(M * d);
   p.qc = w.alloc<bf16>(M * d); p.kvc = w.alloc<bf16>(ML * 2 * d * NL); p.u = w.alloc<bf16>(M * hid);
-  p.tfreq = w.alloc<bf16>((int64_t)Bc * 256); p.t_h = w.alloc<bf16>((int64_t)Bc * d);
-  p.t_silu = w.alloc<bf16>((int64_t)Bc * d);
   p.mem_in = w.alloc<bf16>(ML * d); p.y_h = w.alloc<bf16>(ML * d); p.ymem = w.alloc<bf16>(ML * d);
   p.feat_bf = w.alloc<bf16>(MB * 256); p.text_bf = w.alloc<bf16>(ML * c.text_dim);
   p.vid_bf = w.alloc<bf16>(MB * c.vision_dim);
@@ -631,11 +678,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   p.fused_norm = !getenv("SAB_NO_FUSED_NORM");
   if (p.fused_norm) {
     p.ssq_n = 2 * ((d + 255) / 256);
-    p.nrm_cs = w.alloc<float>((int64_t)2 * NL * Bc * d);
-    p.nrm_shift = w.alloc<bf16>((int64_t)2 * NL * Bc * d);
     p.nrm_ssq = w.alloc<float>(M * p.ssq_n, true);
-    p.nrm_bias_qkv = w.alloc<float>((int64_t)NL * Bc * 3 * d);
-    p.nrm_bias_w13 = w.alloc<float>((int64_t)NL * Bc * 2 * hid);
   }
   p.n_ids_cap = n_ids_cap;
   p.anchor_ids = w.alloc<long long>((int64_t)B * p.n_ids_cap); p.anchor_align = w.alloc<long long>(MB);
@@ -648,13 +691,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   p.g_vid = make_linear("cond.align_video", p.vid_bf, MB, c.vision_dim, e->wvid, d, 256, EPI_AFFINE);
   p.g_vid.P.bias = e->vid_b; p.g_vid.P.out_f32 = p.vproj; p.g_vid.P.out_f32_ld = d;
 
-  // ---- per-evaluation prologue ----
-  p.g_t13 = make_linear("t_embedder.w13", p.tfreq, Bc, 256, e->t_w13, 2 * d, 256, EPI_SWIGLU);
-  p.g_t13.P.out_bf16 = p.t_h; p.g_t13.P.out_bf16_ld = d;
-  p.g_t2 = make_linear("t_embedder.w2", p.t_h, Bc, d, e->t_w2, d, 256, EPI_AFFINE);
-  p.g_t2.P.out_f32 = p.t; p.g_t2.P.out_f32_ld = d;
-  p.g_tb = make_linear("t_block", p.t_silu, Bc, d, e->tb_w, 6 * d, 256, EPI_AFFINE);
-  p.g_tb.P.bias = e->tb_b; p.g_tb.P.out_f32 = p.t0; p.g_tb.P.out_f32_ld = 6 * d;
+  // ---- per-evaluation prologue (the time-only part lives in a TimeState, built on first use) ----
   p.g_y13 = make_linear("y_embedder.w13", p.mem_in, ML, d, e->y_w13, 2 * d, 256, EPI_SWIGLU);
   p.g_y13.P.out_bf16 = p.y_h; p.g_y13.P.out_bf16_ld = d;
   p.g_y2 = make_linear("y_embedder.w2", p.y_h, ML, d, e->y_w2, d, 256, EPI_AFFINE);
@@ -674,15 +711,16 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   // xn) and the partial sums of squares; `which` = 2l (attention_norm of layer l) or 2l+1 (ffn_norm)
   auto norm_producer = [&](GemmOp& op, int which) {
     if (!p.fused_norm) return;
+    (void)which;                  // colscale (TimeState row) is bound per evaluation in dit_eval
     op.mode = EPI_AFFINE_NORM;
-    op.P.colscale = p.nrm_cs + (int64_t)which * Bc * d; op.P.colscale_ld = d; op.P.gate_div = T;
+    op.P.gate_div = T;
     op.P.out_scaled = p.xn; op.P.out_scaled_ld = d;
     op.P.ssq_out = p.nrm_ssq; op.P.ssq_ld = p.ssq_n;
   };
-  auto norm_consumer = [&](GemmOp& op, const float* bias, long long bias_ld) {
+  auto norm_consumer = [&](GemmOp& op) {   // ibias (TimeState row) is bound per evaluation in dit_eval
     if (!p.fused_norm) return;
     op.P.ssq_in = p.nrm_ssq; op.P.ssq_n = p.ssq_n; op.P.ssq_inv_dim = 1.0f / (float)d;
-    op.P.ibias = bias; op.P.ibias_ld = bias_ld; op.P.ibias_div = T;
+    op.P.ibias_div = T;
   };
   norm_producer(p.g_xe[1], 0);
   // ---- layers ----
@@ -691,16 +729,15 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   for (int l = 0; l < NL; ++l) {
     const LayerW& W = e->layers[l];
     LayerOps& o = p.lay[l];
-    float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
     const long long kv_ld = 2LL * d * NL;            // layer l's K|V live at columns [l*2d, (l+1)*2d) of p.kvc
     bf16* kvc_l = p.kvc + (long long)l * 2 * d;
     o.qkv = make_linear("attention.qkv", p.xn, M, d, W.wqkv, 3 * d, 256, EPI_QKV);
     o.qkv.P.out_bf16 = p.qkv; o.qkv.P.out_bf16_ld = 3 * d;
     o.qkv.P.qnorm_w = W.qn_scaled; o.qkv.P.knorm_w = W.kn; o.qkv.P.n_q_end = d; o.qkv.P.n_k_end = 2 * d;
     o.qkv.P.rope = e->rope; o.qkv.P.rope_T = T; o.qkv.P.use_rope = 1; o.qkv.P.eps = c.norm_eps;
-    norm_consumer(o.qkv, p.nrm_bias_qkv ? p.nrm_bias_qkv + (int64_t)l * Bc * 3 * d : nullptr, 3LL * d);
+    norm_consumer(o.qkv);
     o.wo = make_linear("attention.wo", p.att, M, d, W.wo, d, 256, EPI_AFFINE);
-    o.wo.P.gate = mod_l + 2 * d; o.wo.P.gate_ld = 6 * d; o.wo.P.gate_div = T;
+    o.wo.P.gate_div = T;     // gate rows (adaLN gate_msa / gate_mlp of the TimeState) are bound per evaluation
     o.wo.P.res = p.h; o.wo.P.res_ld = d; o.wo.P.out_f32 = p.h; o.wo.P.out_f32_ld = d;
     o.wo.P.out_bf16 = p.hb; o.wo.P.out_bf16_ld = d;
     o.q_c = make_linear("cross.wq", p.hb, M, d, W.wq_c, d, 256, EPI_QKV);
@@ -723,20 +760,11 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
     norm_producer(o.wo_c, 2 * l + 1);
     o.w13 = make_linear("ffn.w13", p.xn, M, d, W.w13, 2 * hid, 256, EPI_SWIGLU);
     o.w13.P.out_bf16 = p.u; o.w13.P.out_bf16_ld = hid; o.w13.P.eps = c.norm_eps;
-    norm_consumer(o.w13, p.nrm_bias_w13 ? p.nrm_bias_w13 + (int64_t)l * Bc * 2 * hid : nullptr, 2LL * hid);
+    norm_consumer(o.w13);
     o.w2 = make_linear("ffn.w2", p.u, M, hid, W.w2, d, 256, EPI_AFFINE);
-    o.w2.P.gate = mod_l + 5 * d; o.w2.P.gate_ld = 6 * d; o.w2.P.gate_div = T;
+    o.w2.P.gate_div = T;
     o.w2.P.res = p.h; o.w2.P.res_ld = d; o.w2.P.out_f32 = p.h; o.w2.P.out_f32_ld = d;
     if (l + 1 < NL) norm_producer(o.w2, 2 * (l + 1));      // the last layer feeds the final norm (standalone kernel)
-    if (p.fused_norm) {
-      // shift @ W^T: [Bc, d] x [N, d]^T with the SAME packed weights as the main GEMM (so the bias columns line up
-      // with its accumulator columns, head permutation and gate/up interleave included).  Weight-streaming (HBM) bound
-      // at M = Bc rows: 64-column tiles so that every SM pulls a share of the weight
-      o.bias_qkv = make_linear("norm.bias.qkv", p.nrm_shift + (int64_t)(2 * l) * Bc * d, Bc, d, W.wqkv, 3 * d, 64, EPI_AFFINE);
-      o.bias_qkv.P.out_f32 = p.nrm_bias_qkv + (int64_t)l * Bc * 3 * d; o.bias_qkv.P.out_f32_ld = 3 * d;
-      o.bias_w13 = make_linear("norm.bias.w13", p.nrm_shift + (int64_t)(2 * l + 1) * Bc * d, Bc, d, W.w13, 2 * hid, 64, EPI_AFFINE);
-      o.bias_w13.P.out_f32 = p.nrm_bias_w13 + (int64_t)l * Bc * 2 * hid; o.bias_w13.P.out_f32_ld = 2 * hid;
-    }
   }
   p.g_out = make_linear("output", p.xn, M, d, e->w_out, c.out_channels, 256, EPI_AFFINE);
   // every layer's text K|V in one GEMM per evaluation: [Bc*L, d] x [NL*2d, d]^T, k-norm per layer
@@ -753,7 +781,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   }
 
   // algorithmic FLOPs of one evaluation (GEMMs + attention), for roofline reporting
-  double f = p.g_kvc_all.flops + p.g_t13.flops + p.g_t2.flops + p.g_tb.flops + p.g_y13.flops + p.g_y2.flops + p.g_in.flops +
+  double f = p.g_kvc_all.flops + p.g_y13.flops + p.g_y2.flops + p.g_in.flops +
              p.g_xe[0].flops + p.g_xe[1].flops + p.g_out.flops;
   for (auto& o : p.lay)
     f += o.qkv.flops + o.wo.flops + o.q_c.flops + o.wo_c.flops + o.w13.flops + o.w2.flops +
@@ -872,30 +900,49 @@ struct FinalSpec {
   bf16* out_bf16;      // next evaluation's GEMM operand (or nullptr)
 };
 
-static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, cudaStream_t st) {
-  DitPlan& p = *e->dit;
+// the time-only part of an evaluation for the R rows of a TimeState (ts.time holds the R times)
+static void run_time_state(sab_engine* e, DitPlan& p, TimeState& ts, cudaStream_t st) {
   const sab_config& c = e->cfg;
-  const int d = c.dim, Bc = p.Bc, T = p.T, L = p.L, NL = c.n_layers, H = c.n_heads, cand = p.cand;
-  const int M = (int)p.M;
-  const float sl2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
-
+  const int d = c.dim, NL = c.n_layers, R = ts.R;
   mark(e, st, "time_features_kernel");
-  time_features_kernel<<<256, 256, 0, st>>>(time_dev, Bc, cand, d, L, p.tfreq, p.mem_base, p.mem_in);
-  gemm(e, p.g_t13, st);
-  gemm(e, p.g_t2, st);
+  tfreq_kernel<<<(R * 256 + 255) / 256, 256, 0, st>>>(ts.time, R, ts.tfreq);
+  gemm(e, ts.g_t13, st);
+  gemm(e, ts.g_t2, st);
   mark(e, st, "silu_cast_kernel");
-  silu_cast_kernel<<<64, 256, 0, st>>>(p.t, p.t_silu, (long long)Bc * d);
-  gemm(e, p.g_tb, st);
+  silu_cast_kernel<<<64, 256, 0, st>>>(ts.t, ts.t_silu, (long long)R * d);
+  gemm(e, ts.g_tb, st);
   mark(e, st, "build_mod_kernel");
-  build_mod_kernel<<<512, 256, 0, st>>>(e->tables, p.t0, p.mod, NL, Bc, d, e->final_table, p.t, p.fin);
+  build_mod_kernel<<<512, 256, 0, st>>>(e->tables, ts.t0, ts.mod, NL, R, d, e->final_table, ts.t, ts.fin);
   if (p.fused_norm) {
     mark(e, st, "norm_tables_kernel");
-    norm_tables_kernel<<<512, 256, 0, st>>>(p.mod, e->norm_w_all, NL, Bc, d, p.nrm_cs, p.nrm_shift);
+    norm_tables_kernel<<<512, 256, 0, st>>>(ts.mod, e->norm_w_all, NL, R, d, ts.cs, ts.shift);
     for (int l = 0; l < NL; ++l) {
-      gemm(e, p.lay[l].bias_qkv, st);
-      gemm(e, p.lay[l].bias_w13, st);
+      gemm(e, ts.g_bias_qkv[l], st);
+      gemm(e, ts.g_bias_w13[l], st);
     }
   }
+  SAB_CUDA(cudaGetLastError());
+}
+
+// One evaluation.  `row` < 0: ts has one row per sequence (per-item adaLN state); `row` >= 0: ts row `row` holds the
+// state of this evaluation's time, shared by every sequence (item stride 0).  time_dev: the Bc times (text memory).
+static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, const TimeState& ts, int row,
+                     cudaStream_t st) {
+  DitPlan& p = *e->dit;
+  const sab_config& c = e->cfg;
+  const int d = c.dim, Bc = p.Bc, T = p.T, L = p.L, NL = c.n_layers, H = c.n_heads, cand = p.cand, hid = c.ffn_hidden;
+  const int M = (int)p.M;
+  const float sl2 = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
+  const int R = ts.R, r0 = row < 0 ? 0 : row;
+  const int istride = row < 0 ? 1 : 0;        // per-item tables advance by one row per sequence, shared ones do not
+  auto mod_row = [&](int l, int r) { return ts.mod + (((int64_t)l * R + r0) * 6 + r) * d; };
+  auto bind_gate = [&](GemmOp& op, int l, int r) { op.P.gate = mod_row(l, r); op.P.gate_ld = istride * 6 * d; };
+  auto bind_cs = [&](GemmOp& op, int which) {
+    if (p.fused_norm) { op.P.colscale = ts.cs + ((int64_t)which * R + r0) * d; op.P.colscale_ld = (long long)istride * d; }
+  };
+
+  mark(e, st, "mem_time_kernel");
+  mem_time_kernel<<<256, 256, 0, st>>>(time_dev, Bc, cand, d, L, p.mem_base, p.mem_in);
   gemm(e, p.g_y13, st);
   gemm(e, p.g_y2, st);
   gemm(e, p.g_in, st);
@@ -907,19 +954,28 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
     mark(e, st, "gn_silu_kernel");
     gn_silu_kernel<<<dim3(64, Bc), 256, 0, st>>>(src, p.gn_partial, e->xe_gn_w[b], e->xe_gn_b[b], d, (long long)T * d,
                                                1e-5f, p.gn_a);
-    gemm(e, p.g_xe[b], st);
+    GemmOp xe = p.g_xe[b];
+    if (b == 1) bind_cs(xe, 0);
+    gemm(e, xe, st);
   }
   SAB_CUDA(cudaGetLastError());
   gemm(e, p.g_kvc_all, st);
   int dir = 1;   // x_embedder.conv2 (the producer of h) walked the rows forwards
   for (int l = 0; l < NL; ++l) {
     const LayerW& W = e->layers[l];
-    LayerOps& o = p.lay[l];
-    const float* mod_l = p.mod + (int64_t)l * Bc * 6 * d;
+    LayerOps o = p.lay[l];      // by value: the TimeState rows of this evaluation are bound below
+    const long long mod_ld = (long long)istride * 6 * d;
     if (!p.fused_norm) {
-      rmsnorm_mod(e, p.h, W.attn_norm, mod_l, mod_l + d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
+      rmsnorm_mod(e, p.h, W.attn_norm, mod_row(l, 0), mod_row(l, 1), mod_ld, T, p.xn, M, st, g_serpentine ? dir : 0);
       dir ^= 1;
+    } else {
+      o.qkv.P.ibias = ts.bias_qkv + ((int64_t)l * R + r0) * 3 * d; o.qkv.P.ibias_ld = (long long)istride * 3 * d;
+      o.w13.P.ibias = ts.bias_w13 + ((int64_t)l * R + r0) * 2 * hid; o.w13.P.ibias_ld = (long long)istride * 2 * hid;
+      bind_cs(o.wo_c, 2 * l + 1);
+      if (l + 1 < NL) bind_cs(o.w2, 2 * (l + 1));
     }
+    bind_gate(o.wo, l, 2);
+    bind_gate(o.w2, l, 5);
     gemm_dir(e, o.qkv, dir, st);
     AttnParams a{};
     a.q = p.qkv; a.q_ld = 3 * d; a.q_col0 = 0;
@@ -960,13 +1016,14 @@ static void dit_eval(sab_engine* e, const float* time_dev, const FinalSpec& fs, 
     }
     gemm_dir(e, o.wo_c, dir, st);
     if (!p.fused_norm) {
-      rmsnorm_mod(e, p.h, W.ffn_norm, mod_l + 3 * d, mod_l + 4 * d, 6LL * d, T, p.xn, M, st, g_serpentine ? dir : 0);
+      rmsnorm_mod(e, p.h, W.ffn_norm, mod_row(l, 3), mod_row(l, 4), mod_ld, T, p.xn, M, st, g_serpentine ? dir : 0);
       dir ^= 1;
     }
     gemm_dir(e, o.w13, dir, st);
     gemm_dir(e, o.w2, dir, st);
   }
-  rmsnorm_mod(e, p.h, e->final_norm, p.fin, p.fin + d, 2LL * d, T, p.xn, M, st);
+  rmsnorm_mod(e, p.h, e->final_norm, ts.fin + (int64_t)r0 * 2 * d, ts.fin + (int64_t)r0 * 2 * d + d, (long long)istride * 2 * d, T,
+              p.xn, M, st);
   GemmOp out = p.g_out;
   out.P.res = fs.base; out.P.res_ld = 256; out.P.alpha = fs.coef;
   out.P.out_f32 = fs.out_f32; out.P.out_f32_ld = 256;
@@ -1314,6 +1371,7 @@ int sab_load_weight(sab_engine* e, const char* name, const float* data, const in
   if (!is_device) SAB_CUDA(cudaStreamSynchronize(st));  // staging buffer is reused by the next call
   s.loaded = true;
   e->finalized = false;
+  if (e->dit) e->dit->ts_solve.valid = false;           // hoisted adaLN tables depend on the weights
   SAB_API_END
 }
 
@@ -1430,7 +1488,10 @@ int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float*
   mark(e, st, "cast_bf16_kernel");
   cast_bf16_kernel<<<512, 256, 0, st>>>(noisy, p.y_bf, p.M * 256);
   FinalSpec fs{nullptr, 1.f, velocity, nullptr};
-  dit_eval(e, time, fs, st);
+  if (p.ts_item.R == 0) build_time_state(e, p, p.ts_item, p.Bc);
+  SAB_CUDA(cudaMemcpyAsync(p.ts_item.time, time, (size_t)p.Bc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  run_time_state(e, p, p.ts_item, st);
+  dit_eval(e, time, fs, p.ts_item, -1, st);
   SAB_API_END
 }
 
@@ -1453,6 +1514,24 @@ int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, voi
     SAB_CUDA(cudaStreamSynchronize(st));  // `times` is a stack-owned host buffer
     p.time_steps_uploaded = n_steps;
   }
+  // The adaLN state depends on the evaluation time only and every sequence of a solve shares it: one row per
+  // evaluation, computed once per (plan, step count, weights) instead of 2*n_steps times per call inside the loop.
+  if (p.ts_solve.R != 2 * n_steps) {
+    if (p.ts_solve.R != 0) SAB_CUDA(cudaStreamSynchronize(st));
+    p.ts_solve = TimeState();     // a new step count: new tables (the old buffers stay with the plan's pool)
+    build_time_state(e, p, p.ts_solve, 2 * n_steps);
+  }
+  if (!p.ts_solve.valid) {
+    std::vector<float> tk((size_t)2 * n_steps);
+    for (int k = 0; k < n_steps; ++k) {
+      tk[2 * k] = (float)k / (float)n_steps;
+      tk[2 * k + 1] = ((float)k + 0.5f) / (float)n_steps;
+    }
+    SAB_CUDA(cudaMemcpyAsync(p.ts_solve.time, tk.data(), tk.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    SAB_CUDA(cudaStreamSynchronize(st));
+    run_time_state(e, p, p.ts_solve, st);
+    p.ts_solve.valid = true;
+  }
   SAB_CUDA(cudaMemcpyAsync(p.y, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   auto enqueue = [&](cudaStream_t st) {
     mark(e, st, "cast_bf16_kernel");
@@ -1461,9 +1540,9 @@ int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, voi
     for (int k = 0; k < n_steps; ++k) {
       // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)
       FinalSpec a{p.y, 0.5f * dt, p.ymid, p.y_bf};
-      dit_eval(e, p.time_dev + (size_t)(2 * k) * p.Bc, a, st);
+      dit_eval(e, p.time_dev + (size_t)(2 * k) * p.Bc, a, p.ts_solve, 2 * k, st);
       FinalSpec b{p.y, dt, p.y, p.y_bf};
-      dit_eval(e, p.time_dev + (size_t)(2 * k + 1) * p.Bc, b, st);
+      dit_eval(e, p.time_dev + (size_t)(2 * k + 1) * p.Bc, b, p.ts_solve, 2 * k + 1, st);
     }
   };
   static const bool use_graph = !getenv("SAB_NO_GRAPH");
