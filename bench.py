@@ -299,7 +299,7 @@ def run_gpu(args):
     from sam_audio_b200 import SAMAudioProcessor
     from sam_audio_b200.config import stand_in_config
     from sam_audio_b200.model import SAMAudio
-    from sam_audio_b200.parallel import all_gather_waveforms, broadcast_state_dict
+    from sam_audio_b200.parallel import all_gather_waveforms, broadcast_state_dict, separate_and_gather
     from sam_audio_b200.synthetic import (make_state_dict, synthetic_clip, synthetic_descriptions, synthetic_noise)
     from sam_audio_b200.text_encoder import T5TextEncoder
 
@@ -342,21 +342,22 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_resident(batch, noise):
-        out = model.separate(batch, noise=noise, reranking_candidates=C)
-        if world > 1:
-            loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])
-            return all_gather_waveforms(loc, [B] * world)
-        return out
+        if world > 1:       # the all-gather of each decoded chunk runs under the next chunk's decode
+            return separate_and_gather(model, batch, noise, [B] * world, reranking_candidates=C)
+        return model.separate(batch, noise=noise, reranking_candidates=C)
 
     def step_e2e():
         batch = proc(descriptions=desc, audios=clips)               # host: mono mix, pad, masks, anchors
         if not batch.audios.is_pinned():
             batch.audios = batch.audios.pin_memory()
         batch = batch.to(dev)                                       # H2D
-        out = model.separate(batch, noise=noise_host.to(dev, non_blocking=True), reranking_candidates=C)
-        loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])
+        nz = noise_host.to(dev, non_blocking=True)
         if world > 1:
-            all_gather_waveforms(loc, [B] * world)
+            full = separate_and_gather(model, batch, nz, [B] * world, reranking_candidates=C)
+            loc = full[rank * B:(rank + 1) * B]
+        else:
+            out = model.separate(batch, noise=nz, reranking_candidates=C)
+            loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])
         out_host.copy_(loc, non_blocking=True)                      # D2H of the step's result
         torch.cuda.current_stream().synchronize()
         return out_host

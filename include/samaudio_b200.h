@@ -96,9 +96,13 @@ int sab_prepare(sab_engine* e, int B, int candidates, int T, int L, const float*
  * noisy [Bc, T, 256], time [Bc] (device), velocity out [Bc, T, 256]. */
 int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float* velocity, void* stream);
 
-/* The ODE solve.  replaces: torchdiffeq.odeint(method="midpoint", step_size=1/n_steps) as called at
- * model.py:285-290 (2*n_steps evaluations).  noise [Bc, T, 256] in, latent [Bc, T, 256] out (may alias). */
-int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, void* stream);
+/* The ODE solve.  replaces: torchdiffeq.odeint(method=..., options={"step_size": 1/n_steps}) as called at
+ * model.py:285-290 with the reference's **ode_opt: fixed-grid midpoint (the default, 2*n_steps evaluations), euler
+ * (n_steps) or rk4 (torchdiffeq's 3/8 rule, 4*n_steps).  noise [Bc, T, 256] in, latent [Bc, T, 256] out (may alias). */
+#define SAB_ODE_MIDPOINT 0
+#define SAB_ODE_EULER 1
+#define SAB_ODE_RK4 2
+int sab_solve(sab_engine* e, const float* noise, int n_steps, int method, float* latent, void* stream);
 
 /* Codec synthesis.  replaces: DACVAE.decode (codec.py:86-89) as called at model.py:291-295.
  * latent [Bc, T, 256] (target half = channels [0,128), residual half = [128,256));
@@ -160,6 +164,13 @@ int sab_test_attention_tc(int items, int heads, int T, const void* q, const void
  * trace: null, or a device buffer of 8 x 32 x 8 int64 that CTA 0 fills with clock64() stamps (tools/attn_trace.py). */
 int sab_test_attention_tc2(int items, int heads, int T, const void* q_bf16, const void* k_bf16, const void* v_bf16,
                            const uint8_t* key_mask, void* o_bf16, float shift_log2, int poly, long long* trace, void* stream);
+
+/* Visual prompting, frame pre-processing.  replaces: PerceptionEncoder.get_transform (vision_encoder.py:91-113) =
+ * torchvision Resize((S, S), BICUBIC, antialias) on uint8 frames, x / 255, Normalize(0.5, 0.5).
+ * frames [n_frames, 3, H, W] uint8 (device), workspace [n_frames, 3, H, S] fp32 (device), out [n_frames, 3, S, S] fp32.
+ * Engine-independent (no weights). */
+int sab_preprocess_frames(const uint8_t* frames, int n_frames, int H, int W, int out_size, float* workspace, float* out,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,19 @@ class _SyntheticText(torch.nn.Module):
         return synthetic.synthetic_text_features(texts)
 
 
+class FakeClip:
+    """Stands in for core.vision_encoder.pe.CLIP (third-party, absent): 12x12 average pooling -> fixed random
+    projection -> optional L2 normalisation.  Only the reference's wrapper logic around it is under test."""
+    DIM = 32
+
+    def __init__(self):
+        self.proj = torch.randn(3 * 12 * 12, self.DIM, generator=torch.Generator().manual_seed(5)) / 20.0
+
+    def encode_image(self, x, normalize=True):
+        f = torch.nn.functional.adaptive_avg_pool2d(x.float(), 12).flatten(1) @ self.proj.to(x.device)
+        return torch.nn.functional.normalize(f, dim=-1) if normalize else f
+
+
 def build_reference_pipeline(ref, cfg, sd):
     """SAMAudio.__new__ + attach the reference's own sub-modules."""
     from sam_audio.model import model as ref_model
@@ -189,6 +202,27 @@ def main():
     torch.save(dict(noisy=noisy, feats=feats, text=text, video=video, time=time, text_mask=mem_mask,
                     anchor_ids=ids, anchor_alignment=al, pad_mask=pad_mask, out=outs),
                os.path.join(GOLDEN, "samaudio_forward_tiny.pt"))
+
+    # ---------------- visual prompting: PerceptionEncoder transform + chunked encode (reference classes) ----------------
+    from sam_audio.model import vision_encoder as ref_ve
+    from sam_audio.model.config import PerceptionEncoderConfig as RefPEC
+    fake = FakeClip()
+    ref_ve.pe.CLIP = type("CLIP", (), {"from_config": staticmethod(lambda name: fake)})   # the third-party tower: a stand-in
+    enc = ref_ve.PerceptionEncoder(RefPEC(dim=FakeClip.DIM))
+    gv2 = torch.Generator().manual_seed(78)
+    vids = [torch.randint(0, 256, (n, 3, 20, 28), generator=gv2, dtype=torch.uint8) for n in (310, 7, 1)]
+    feats = enc(vids)                                             # 310 frames > batch_size 300: two chunks; zero-padded
+    o = restate.vision_encode(vids, lambda x: fake.encode_image(x, normalize=True), 336, 300)
+    assert feats.shape == (3, 310, FakeClip.DIM) and rel_l2(o, feats) < 1e-4, rel_l2(o, feats)
+    big = torch.randint(0, 256, (2, 3, 360, 640), generator=gv2, dtype=torch.uint8)
+    tb = enc.transform(big)                                       # the reference's own torchvision transform
+    lvl = ((tb * 0.5 + 0.5) * 255).round().to(torch.uint8)
+    mine = restate.frame_transform(big)
+    mis = float((((mine * 0.5 + 0.5) * 255).round().to(torch.uint8) != lvl).float().mean())
+    print(f"vision: chunked encode ok; frame transform vs torchvision: {mis:.2e} of the uint8 levels differ (by 1)")
+    assert mis < 1e-4
+    torch.save(dict(video_lens=[310, 7, 1], seed=78, feats=feats, big_levels=lvl, proj=fake.proj),
+               os.path.join(GOLDEN, "vision.pt"))
 
     # ---------------- separate(): control flow, candidates, unbatch ----------------
     lens2 = [24000, 15000]

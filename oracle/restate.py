@@ -237,6 +237,28 @@ def odeint_midpoint(f: Callable, y0, n_steps: int = 16):
     return y
 
 
+def odeint_fixed(f: Callable, y0, n_steps: int = 16, method: str = "midpoint"):
+    """The fixed-grid solvers the reference can select through **ode_opt (model.py:285-290 -> torchdiffeq.odeint).
+    torchdiffeq's source is absent here (PARITY UNPINNED: restated from its published fixed_grid.py / rk_common.py):
+    euler  y += dt f(t, y);  midpoint as above;  rk4 = the 3/8 rule (rk4_alt_step_func)."""
+    if method == "midpoint":
+        return odeint_midpoint(f, y0, n_steps)
+    y, dt = y0, 1.0 / n_steps
+    for k in range(n_steps):
+        t0 = torch.tensor(k * dt)
+        if method == "euler":
+            y = y + dt * f(t0, y)
+        elif method == "rk4":
+            k1 = f(t0, y)
+            k2 = f(t0 + dt / 3, y + dt * k1 / 3)
+            k3 = f(t0 + dt * 2 / 3, y + dt * (k2 - k1 / 3))
+            k4 = f(t0 + dt, y + dt * (k1 - k2 + k3))
+            y = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+        else:
+            raise ValueError(method)
+    return y
+
+
 # ----------------------------------------------------------------------------
 # DAC-VAE codec (PARITY UNPINNED: restated from the Descript-DAC layout)
 # ----------------------------------------------------------------------------
@@ -293,11 +315,80 @@ def codec_decode(sd: SD, ccfg, z, prefix="audio_codec"):
 
 
 # ----------------------------------------------------------------------------
+# visual prompting: frame transform + chunked encoding (vision_encoder.py:47-69, 91-113)
+# ----------------------------------------------------------------------------
+def _aa_cubic_taps(in_size: int, out_size: int):
+    """Tap window and normalised weights per output index of torch's antialiased bicubic (the kernel torchvision's
+    Resize(..., BICUBIC, antialias=True) reaches through F.interpolate): PIL-style cubic a = -1/2, support and filter
+    stretched by scale = in/out when down-sampling; all arithmetic in float32 (restated from the published ATen
+    algorithm, aten/native/cpu/UpSampleKernel.cpp; pinned against torchvision by tests/test_oracle_vision.py)."""
+    import numpy as np
+    f = np.float32
+    scale = f(in_size) / f(out_size)
+    support = f(2.0) * scale if scale >= 1 else f(2.0)
+    invscale = f(1.0) / scale if scale >= 1 else f(1.0)
+    a = f(-0.5)
+    out = []
+    for i in range(out_size):
+        center = scale * f(i + 0.5)
+        lo = max(int(center - support + f(0.5)), 0)
+        n = min(int(center + support + f(0.5)), in_size) - lo
+        ws, tot = [], f(0)
+        for j in range(n):
+            x = f(abs(f(j + lo) - center + f(0.5)) * invscale)
+            if x < 1:
+                w = ((a + f(2)) * x - (a + f(3))) * x * x + f(1)
+            elif x < 2:
+                w = (((x - f(5)) * x + f(8)) * x - f(4)) * a
+            else:
+                w = f(0)
+            ws.append(f(w))
+            tot = f(tot + f(w))
+        out.append((lo, [f(w / tot) for w in ws]))
+    return out
+
+
+def _resize_axis(x: torch.Tensor, out_size: int, axis: int) -> torch.Tensor:
+    x = x.movedim(axis, -1)
+    res = torch.empty(*x.shape[:-1], out_size, dtype=torch.float32)
+    for i, (lo, ws) in enumerate(_aa_cubic_taps(x.shape[-1], out_size)):
+        t = x[..., lo] * float(ws[0])
+        for j in range(1, len(ws)):
+            t = t + x[..., lo + j] * float(ws[j])           # separate multiply / add, in tap order
+        res[..., i] = t
+    return res.movedim(-1, axis)
+
+
+def frame_transform(video_u8: torch.Tensor, size: int = 336) -> torch.Tensor:
+    """vision_encoder.py:91-113: Resize((size, size), BICUBIC) [antialias, uint8 in -> uint8 out], x/255,
+    Normalize(.5, .5).  [T, 3, H, W] uint8 -> [T, 3, size, size] float32.  Width first, then height."""
+    x = _resize_axis(_resize_axis(video_u8.float(), size, 3), size, 2)
+    x = x.clamp(0, 255).round()                             # torchvision: clamp, round, cast to uint8
+    return (x / 255.0 - 0.5) / 0.5
+
+
+def vision_encode(videos, encode: Callable, size: int = 336, batch_size: int = 300, transform=frame_transform):
+    """vision_encoder.py:47-69: per video transform, encode in chunks of batch_size frames, zero-pad to the longest."""
+    feats = []
+    for v in videos:
+        x = transform(v, size)
+        if batch_size > 0 and x.shape[0] > batch_size:
+            feats.append(torch.cat([encode(x[i:i + batch_size]) for i in range(0, x.shape[0], batch_size)], 0))
+        else:
+            feats.append(encode(x))
+    T = max(f.shape[0] for f in feats)
+    out = feats[0].new_zeros(len(feats), T, feats[0].shape[-1])
+    for i, f in enumerate(feats):
+        out[i, : f.shape[0]] = f
+    return out
+
+
+# ----------------------------------------------------------------------------
 # separate()
 # ----------------------------------------------------------------------------
 def separate(sd: SD, cfg, audios, pad_mask, sizes, text_features, text_mask, anchor_ids,
              anchor_alignment, noise, video_features=None, candidates: int = 1, n_steps: int = 16,
-             return_latent=False):
+             return_latent=False, method: str = "midpoint"):
     """model.py:247-338 with rankers None (candidate 0; config.py:214-215, model.py:329-330).
     audios [B,1,S] fp32; returns (target list, residual list[, latent])."""
     cc = cfg.audio_codec
@@ -317,7 +408,7 @@ def separate(sd: SD, cfg, audios, pad_mask, sizes, text_features, text_mask, anc
     def field(t, y):
         return samaudio_forward(sd, cfg, y, time=t.expand(y.shape[0]), **fa)
 
-    lat = odeint_midpoint(field, noise, n_steps)
+    lat = odeint_fixed(field, noise, n_steps, method)
     Bc = lat.shape[0]
     wavs = codec_decode(sd, cc, lat.transpose(1, 2).reshape(2 * Bc, cc.codebook_dim, T)).view(Bc, 2, -1)
     n = (sizes * cc.hop_length).int()                                  # codec.py:91-97

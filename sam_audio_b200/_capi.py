@@ -39,7 +39,7 @@ class SabT5Config(ctypes.Structure):
 EXPORTS = [
     "sab_last_error", "sab_version", "sab_create", "sab_destroy", "sab_load_weight", "sab_finalize_weights",
     "sab_encode", "sab_prepare", "sab_dit_forward", "sab_solve", "sab_decode", "sab_launch_count",
-    "sab_workspace_bytes", "sab_profile", "sab_profile_report", "sab_test_gemm", "sab_test_attention", "sab_test_attention_tc", "sab_test_attention_tc2",
+    "sab_workspace_bytes", "sab_profile", "sab_profile_report", "sab_test_gemm", "sab_test_attention", "sab_test_attention_tc", "sab_test_attention_tc2", "sab_preprocess_frames",
     "sab_t5_create", "sab_t5_destroy", "sab_t5_load_weight", "sab_t5_finalize", "sab_t5_forward", "sab_t5_launch_count",
 ]
 
@@ -66,7 +66,7 @@ def lib() -> ctypes.CDLL:
         L.sab_encode.argtypes = [vp, vp, i32, i64, vp, vp]
         L.sab_prepare.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]
         L.sab_dit_forward.argtypes = [vp, vp, vp, vp, vp]
-        L.sab_solve.argtypes = [vp, vp, i32, vp, vp]
+        L.sab_solve.argtypes = [vp, vp, i32, i32, vp, vp]
         L.sab_decode.argtypes = [vp, vp, i32, i32, vp, vp]
         L.sab_launch_count.argtypes = [vp, i32]
         L.sab_launch_count.restype = i64
@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
         L.sab_test_attention.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         L.sab_test_attention_tc.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp]
         L.sab_test_attention_tc2.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, ctypes.c_float, i32, vp, vp]
+        L.sab_preprocess_frames.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
         L.sab_t5_create.argtypes = [ctypes.POINTER(SabT5Config), i32, ctypes.POINTER(vp)]
         L.sab_t5_destroy.argtypes = [vp]
         L.sab_t5_load_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, i32, vp]
@@ -123,6 +124,18 @@ def make_config(cfg) -> SabConfig:
     for i, r in enumerate(cc.decoder_rates):
         c.codec_decoder_rates[i] = r
     return c
+
+
+def preprocess_frames(frames: torch.Tensor, out_size: int) -> torch.Tensor:
+    """uint8 [N, 3, H, W] (cuda) -> fp32 [N, 3, S, S]: antialiased bicubic resize, uint8 rounding, (x/255 - .5)/.5."""
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[1] == 3
+    frames = frames.contiguous()
+    n, _, h, w = frames.shape
+    out = torch.empty(n, 3, out_size, out_size, device=frames.device, dtype=torch.float32)
+    ws = torch.empty(n, 3, h, out_size, device=frames.device, dtype=torch.float32)
+    with torch.cuda.device(frames.device):
+        check(lib().sab_preprocess_frames(frames.data_ptr(), n, h, w, out_size, ws.data_ptr(), out.data_ptr(), stream_ptr()))
+    return out
 
 
 class Engine:
@@ -173,8 +186,10 @@ class Engine:
     def dit_forward(self, noisy, time, out):
         check(lib().sab_dit_forward(self._h, noisy.data_ptr(), time.data_ptr(), out.data_ptr(), stream_ptr()))
 
-    def solve(self, noise, n_steps, out):
-        check(lib().sab_solve(self._h, noise.data_ptr(), n_steps, out.data_ptr(), stream_ptr()))
+    ODE_METHODS = {"midpoint": 0, "euler": 1, "rk4": 2}    # include/samaudio_b200.h SAB_ODE_*
+
+    def solve(self, noise, n_steps, out, method: str = "midpoint"):
+        check(lib().sab_solve(self._h, noise.data_ptr(), n_steps, self.ODE_METHODS[method], out.data_ptr(), stream_ptr()))
 
     def decode(self, latent, Bc, T, wav):
         check(lib().sab_decode(self._h, latent.data_ptr(), Bc, T, wav.data_ptr(), stream_ptr()))

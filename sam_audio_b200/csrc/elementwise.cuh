@@ -138,6 +138,21 @@ __global__ void mem_time_kernel(const float* __restrict__ time /*[B*cand]*/, int
   }
 }
 
+// Runge-Kutta stage combination: out = y + a1 k1 + a2 k2 + a3 k3 + a4 k4 (fp32) and its bf16 copy, the operand of the
+// next evaluation's input projection (out may alias y)
+__global__ void ode_combine_kernel(const float* y, const float* __restrict__ k1, float a1, const float* __restrict__ k2,
+                                   float a2, const float* __restrict__ k3, float a3, const float* __restrict__ k4, float a4,
+                                   float* out, __nv_bfloat16* __restrict__ out_bf, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = y[i] + a1 * k1[i];
+    if (a2 != 0.f) v += a2 * k2[i];
+    if (a3 != 0.f) v += a3 * k3[i];
+    if (a4 != 0.f) v += a4 * k4[i];
+    out[i] = v;
+    out_bf[i] = __float2bfloat16(v);
+  }
+}
+
 // silu + cast (transformer.py:492 t_block_non_linearity) fp32 -> bf16
 __global__ void silu_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

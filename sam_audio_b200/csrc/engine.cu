@@ -18,6 +18,7 @@
 #include "attention_tc2.cuh"
 #include "elementwise.cuh"
 #include "codec_kernels.cuh"
+#include "vision_kernels.cuh"
 
 using namespace sab;
 typedef __nv_bfloat16 bf16;
@@ -607,6 +608,9 @@ struct DitPlan {
   int64_t solve_graph_launches = 0;
   int solves = 0;
   int time_steps_uploaded = 0;
+  int solve_method = 0;              // SAB_ODE_* of the cached time tables / captured graph
+  int64_t time_cap = 0;              // capacity of time_dev (floats)
+  float* rk[4] = {nullptr, nullptr, nullptr, nullptr};   // rk4 stage velocities
   ~DitPlan() { if (solve_graph) cudaGraphExecDestroy(solve_graph); }
 };
 
@@ -666,7 +670,7 @@ static void build_dit_plan(sab_engine* e, int B, int cand, int T, int L, int n_i
   p.h = w.alloc<float>(M * d); p.vproj = w.alloc<float>(MB * d);
   p.condB = cand == 1 ? p.cond : w.alloc<float>(MB * d);
   p.mem_base = w.alloc<float>(ML * d);
-  p.time_dev = w.alloc<float>((int64_t)Bc * 64);
+  p.time_dev = w.alloc<float>((int64_t)Bc * 64); p.time_cap = (int64_t)Bc * 64;
   p.y_bf = w.alloc<bf16>(M * 256); p.gn_a = w.alloc<bf16>(M * d); p.hb = w.alloc<bf16>(M * d);
   p.xn = w.alloc<bf16>(M * d); p.qkv = w.alloc<bf16>(M * 3 * d); p.att = w.alloc<bf16>(M * d);
   p.qc = w.alloc<bf16>(M * d); p.kvc = w.alloc<bf16>(ML * 2 * d * NL); p.u = w.alloc<bf16>(M * hid);
@@ -1495,59 +1499,101 @@ int sab_dit_forward(sab_engine* e, const float* noisy, const float* time, float*
   SAB_API_END
 }
 
-int sab_solve(sab_engine* e, const float* noise, int n_steps, float* latent, void* stream) {
+// stage times (fractions of a step) of the fixed-grid solvers torchdiffeq offers and the reference forwards
+// `ode_opt` to (model.py:285-290): euler, midpoint, rk4 (torchdiffeq's rk4 is the 3/8 rule)
+static int solver_stages(int method, float (&frac)[4]) {
+  switch (method) {
+    case SAB_ODE_EULER: frac[0] = 0.f; return 1;
+    case SAB_ODE_MIDPOINT: frac[0] = 0.f; frac[1] = 0.5f; return 2;
+    case SAB_ODE_RK4: frac[0] = 0.f; frac[1] = 1.f / 3.f; frac[2] = 2.f / 3.f; frac[3] = 1.f; return 4;
+    default: throw Error(fmt("unknown ODE method %d (0 midpoint, 1 euler, 2 rk4)", method));
+  }
+}
+
+int sab_solve(sab_engine* e, const float* noise, int n_steps, int method, float* latent, void* stream) {
   SAB_API_BEGIN_E(e)
   SAB_CHECK(e && e->dit, "sab_prepare must be called first");
-  SAB_CHECK(n_steps >= 1 && 2 * n_steps <= 64, "n_steps out of range");
+  float frac[4];
+  const int S = solver_stages(method, frac);
+  const int E = S * n_steps;                   // evaluations per solve
+  SAB_CHECK(n_steps >= 1 && E <= 128, "n_steps out of range");
   cudaStream_t st = (cudaStream_t)stream;
   DitPlan& p = *e->dit;
   const long long n = p.M * 256;
-  // evaluation times k/n and (k + 1/2)/n, broadcast over the batch (model.py:280 t.expand); uploaded once per plan
-  if (p.time_steps_uploaded != n_steps) {
-    std::vector<float> times((size_t)2 * n_steps * p.Bc);
+  // evaluation times (k + frac_s)/n, broadcast over the batch (model.py:280 t.expand); uploaded once per plan
+  if (p.time_steps_uploaded != n_steps || p.solve_method != method) {
+    std::vector<float> times((size_t)E * p.Bc);
     for (int k = 0; k < n_steps; ++k)
-      for (int b = 0; b < p.Bc; ++b) {
-        times[(size_t)(2 * k) * p.Bc + b] = (float)k / (float)n_steps;
-        times[(size_t)(2 * k + 1) * p.Bc + b] = ((float)k + 0.5f) / (float)n_steps;
-      }
+      for (int sg = 0; sg < S; ++sg)
+        for (int b = 0; b < p.Bc; ++b) times[(size_t)(S * k + sg) * p.Bc + b] = ((float)k + frac[sg]) / (float)n_steps;
+    if (p.time_cap < (int64_t)times.size()) {
+      SAB_CUDA(cudaStreamSynchronize(st));
+      p.time_dev = p.pool.alloc<float>((int64_t)times.size());
+      p.time_cap = (int64_t)times.size();
+    }
     SAB_CUDA(cudaMemcpyAsync(p.time_dev, times.data(), times.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     SAB_CUDA(cudaStreamSynchronize(st));  // `times` is a stack-owned host buffer
     p.time_steps_uploaded = n_steps;
   }
   // The adaLN state depends on the evaluation time only and every sequence of a solve shares it: one row per
-  // evaluation, computed once per (plan, step count, weights) instead of 2*n_steps times per call inside the loop.
-  if (p.ts_solve.R != 2 * n_steps) {
+  // evaluation, computed once per (plan, solver, step count, weights) instead of inside the loop.
+  if (p.ts_solve.R != E || p.solve_method != method) {
     if (p.ts_solve.R != 0) SAB_CUDA(cudaStreamSynchronize(st));
-    p.ts_solve = TimeState();     // a new step count: new tables (the old buffers stay with the plan's pool)
-    build_time_state(e, p, p.ts_solve, 2 * n_steps);
+    p.ts_solve = TimeState();     // a new grid: new tables (the old buffers stay with the plan's pool)
+    build_time_state(e, p, p.ts_solve, E);
   }
   if (!p.ts_solve.valid) {
-    std::vector<float> tk((size_t)2 * n_steps);
-    for (int k = 0; k < n_steps; ++k) {
-      tk[2 * k] = (float)k / (float)n_steps;
-      tk[2 * k + 1] = ((float)k + 0.5f) / (float)n_steps;
-    }
+    std::vector<float> tk((size_t)E);
+    for (int k = 0; k < n_steps; ++k)
+      for (int sg = 0; sg < S; ++sg) tk[S * k + sg] = ((float)k + frac[sg]) / (float)n_steps;
     SAB_CUDA(cudaMemcpyAsync(p.ts_solve.time, tk.data(), tk.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     SAB_CUDA(cudaStreamSynchronize(st));
     run_time_state(e, p, p.ts_solve, st);
     p.ts_solve.valid = true;
   }
+  if (method == SAB_ODE_RK4 && !p.rk[0])
+    for (int i = 0; i < 4; ++i) p.rk[i] = p.pool.alloc<float>(n);
+  const bool new_method = p.solve_method != method;
+  p.solve_method = method;
   SAB_CUDA(cudaMemcpyAsync(p.y, noise, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   auto enqueue = [&](cudaStream_t st) {
     mark(e, st, "cast_bf16_kernel");
     cast_bf16_kernel<<<512, 256, 0, st>>>(p.y, p.y_bf, n);
     const float dt = 1.0f / (float)n_steps;
+    auto tm = [&](int ev) { return p.time_dev + (size_t)ev * p.Bc; };
     for (int k = 0; k < n_steps; ++k) {
-      // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)
-      FinalSpec a{p.y, 0.5f * dt, p.ymid, p.y_bf};
-      dit_eval(e, p.time_dev + (size_t)(2 * k) * p.Bc, a, p.ts_solve, 2 * k, st);
-      FinalSpec b{p.y, dt, p.y, p.y_bf};
-      dit_eval(e, p.time_dev + (size_t)(2 * k + 1) * p.Bc, b, p.ts_solve, 2 * k + 1, st);
+      if (method == SAB_ODE_MIDPOINT) {
+        // f0 = f(t_k, y); y_mid = y + f0*dt/2     |     y += dt * f(t_k + dt/2, y_mid)   (axpy fused in the output GEMM)
+        FinalSpec a{p.y, 0.5f * dt, p.ymid, p.y_bf};
+        dit_eval(e, tm(2 * k), a, p.ts_solve, 2 * k, st);
+        FinalSpec b{p.y, dt, p.y, p.y_bf};
+        dit_eval(e, tm(2 * k + 1), b, p.ts_solve, 2 * k + 1, st);
+      } else if (method == SAB_ODE_EULER) {
+        FinalSpec a{p.y, dt, p.y, p.y_bf};         // y += dt * f(t_k, y)
+        dit_eval(e, tm(k), a, p.ts_solve, k, st);
+      } else {
+        // torchdiffeq rk4 (3/8 rule): k1 = f(t, y); k2 = f(t + dt/3, y + dt k1/3); k3 = f(t + 2dt/3, y + dt (k2 - k1/3));
+        // k4 = f(t + dt, y + dt (k1 - k2 + k3)); y += dt (k1 + 3 k2 + 3 k3 + k4) / 8.  The stage inputs need the raw
+        // velocities, so they are combined by a small elementwise kernel instead of the output GEMM's epilogue.
+        const float c3 = dt / 3.f;
+        auto comb = [&](float* out, float a1, float a2, float a3, float a4) {
+          mark(e, st, "ode_combine_kernel");
+          ode_combine_kernel<<<512, 256, 0, st>>>(p.y, p.rk[0], a1, p.rk[1], a2, p.rk[2], a3, p.rk[3], a4, out, p.y_bf, n);
+        };
+        for (int sg = 0; sg < 4; ++sg) {
+          FinalSpec v{nullptr, 1.f, p.rk[sg], nullptr};
+          dit_eval(e, tm(4 * k + sg), v, p.ts_solve, 4 * k + sg, st);
+          if (sg == 0) comb(p.ymid, c3, 0.f, 0.f, 0.f);
+          else if (sg == 1) comb(p.ymid, -c3, dt, 0.f, 0.f);
+          else if (sg == 2) comb(p.ymid, dt, -dt, dt, 0.f);
+          else comb(p.y, dt * 0.125f, dt * 0.375f, dt * 0.375f, dt * 0.125f);
+        }
+      }
     }
   };
   static const bool use_graph = !getenv("SAB_NO_GRAPH");
   const bool graphable = use_graph && !e->prof && p.solves >= 1;
-  if (graphable && (!p.solve_graph || p.solve_graph_steps != n_steps)) {
+  if (graphable && (!p.solve_graph || p.solve_graph_steps != n_steps || new_method)) {
     if (p.solve_graph) { SAB_CUDA(cudaGraphExecDestroy(p.solve_graph)); p.solve_graph = nullptr; }
     const int64_t launches_before = e->launches;
     cudaGraph_t g = nullptr;
@@ -1819,6 +1865,74 @@ int sab_test_attention_tc2(int items, int heads, int T, const void* q, const voi
     throw;
   }
   g_attn_poly = saved;
+  SAB_API_END
+}
+
+// ---- visual prompting: frame pre-processing (vision_kernels.cuh) ----
+// tap windows + normalised weights of one axis, fp32 arithmetic of ATen's _compute_indices_min_size_weights_aa
+// (cubic a = -1/2, antialias: support and filter stretch by scale = in / out when down-sampling)
+struct AaTaps { int taps = 0; std::vector<int> lo, cnt; std::vector<float> w; };
+static AaTaps aa_taps(int in_size, int out_size) {
+  AaTaps t;
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.f ? 2.0f * scale : 2.0f;
+  const float invscale = scale >= 1.f ? 1.0f / scale : 1.0f;
+  t.taps = (int)ceilf(support) * 2 + 1;
+  t.lo.resize(out_size); t.cnt.resize(out_size); t.w.assign((size_t)out_size * t.taps, 0.f);
+  const float a = -0.5f;
+  for (int i = 0; i < out_size; ++i) {
+    const float center = scale * ((float)i + 0.5f);
+    int lo = (int)(center - support + 0.5f);
+    lo = lo < 0 ? 0 : lo;
+    int hi = (int)(center + support + 0.5f);
+    hi = hi > in_size ? in_size : hi;
+    int n = hi - lo;
+    n = n < 0 ? 0 : (n > t.taps ? t.taps : n);
+    float tot = 0.f;
+    float* w = &t.w[(size_t)i * t.taps];
+    for (int j = 0; j < n; ++j) {
+      float x = fabsf(((float)(j + lo) - center + 0.5f)) * invscale;
+      float v;
+      if (x < 1.f) v = ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+      else if (x < 2.f) v = (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+      else v = 0.f;
+      w[j] = v;
+      tot = tot + v;
+    }
+    for (int j = 0; j < n; ++j) w[j] = w[j] / tot;
+    t.lo[i] = lo; t.cnt[i] = n;
+  }
+  return t;
+}
+struct AaTapsDev { int taps; int *lo, *cnt; float* w; };
+static AaTapsDev aa_taps_device(int in_size, int out_size) {   // cached per (device, in, out): a few KB each
+  static std::map<std::array<int, 3>, AaTapsDev> cache;
+  const std::array<int, 3> key = {cur_device(), in_size, out_size};
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const AaTaps h = aa_taps(in_size, out_size);
+  AaTapsDev d{h.taps, nullptr, nullptr, nullptr};
+  SAB_CUDA(cudaMalloc(&d.lo, out_size * sizeof(int)));
+  SAB_CUDA(cudaMalloc(&d.cnt, out_size * sizeof(int)));
+  SAB_CUDA(cudaMalloc(&d.w, h.w.size() * sizeof(float)));
+  SAB_CUDA(cudaMemcpy(d.lo, h.lo.data(), out_size * sizeof(int), cudaMemcpyHostToDevice));
+  SAB_CUDA(cudaMemcpy(d.cnt, h.cnt.data(), out_size * sizeof(int), cudaMemcpyHostToDevice));
+  SAB_CUDA(cudaMemcpy(d.w, h.w.data(), h.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  cache[key] = d;
+  return d;
+}
+
+int sab_preprocess_frames(const uint8_t* frames, int n_frames, int H, int W, int out_size, float* workspace, float* out,
+                          void* stream) {
+  SAB_API_BEGIN
+  SAB_CHECK(frames && out && workspace, "null argument");
+  SAB_CHECK(n_frames >= 1 && H >= 1 && W >= 1 && out_size >= 1 && W <= 48 * 1024, "bad frame shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const AaTapsDev tx = aa_taps_device(W, out_size), ty = aa_taps_device(H, out_size);
+  const int planes = n_frames * 3;
+  resize_rows_kernel<<<dim3(H, planes), 256, W, st>>>(frames, H, W, out_size, tx.lo, tx.cnt, tx.w, tx.taps, workspace);
+  resize_cols_finish_kernel<<<dim3(out_size, planes), 256, 0, st>>>(workspace, H, out_size, ty.lo, ty.cnt, ty.w, ty.taps, out);
+  SAB_CUDA(cudaGetLastError());
   SAB_API_END
 }
 

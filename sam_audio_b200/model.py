@@ -238,12 +238,23 @@ class SAMAudio(torch.nn.Module):
 
     @torch.inference_mode()
     def separate(self, batch: Batch, noise: Optional[torch.Tensor] = None, ode_opt: Dict[str, Any] = DFLT_ODE_OPT,
-                 reranking_candidates: int = 1, predict_spans: bool = False) -> SeparationResult:
+                 reranking_candidates: int = 1, predict_spans: bool = False, _on_decoded=None) -> SeparationResult:
+        """`_on_decoded(i0, i1, wavs)` (private; sam_audio_b200.parallel): called after the waveforms of sequences
+        [i0, i1) are enqueued for decoding, so that a collective on them can overlap the next chunk's decode."""
         eng = self._ensure_engine()
         c = int(reranking_candidates)
-        if ode_opt.get("method", "midpoint") != "midpoint":
-            raise NotImplementedError("only the reference's midpoint solver is implemented")
-        n_steps = round(1.0 / float(ode_opt.get("options", {}).get("step_size", 2 / 32)))
+        # the reference forwards **ode_opt to torchdiffeq.odeint (model.py:285-290); its fixed-grid solvers are built
+        method = ode_opt.get("method", "midpoint")
+        if method not in _capi.Engine.ODE_METHODS:
+            raise NotImplementedError(f"ode method {method!r}: the fixed-grid solvers {sorted(_capi.Engine.ODE_METHODS)} "
+                                      "are implemented (adaptive torchdiffeq solvers are not)")
+        step = ode_opt.get("options", {}).get("step_size")
+        if step is None:
+            raise NotImplementedError("fixed-grid solvers need options={'step_size': ...} (torchdiffeq would otherwise "
+                                      "take ONE step over [0, 1])")
+        n_steps = round(1.0 / float(step))
+        if abs(n_steps * float(step) - 1.0) > 1e-6:
+            raise NotImplementedError(f"step_size {step} does not divide [0, 1]")
 
         feats = self._get_audio_features(batch.audios)                      # [B, T, 256]
         text_features, text_mask = self.text_encoder(batch.descriptions)
@@ -269,8 +280,15 @@ class SAMAudio(torch.nn.Module):
         hop = self.cfg.audio_codec.hop_length
         wavs = torch.empty(B * c, 2, T * hop, device=feats.device, dtype=torch.float32)
         with torch.cuda.device(feats.device):
-            eng.solve(noise, n_steps, latent)
-            eng.decode(latent, B * c, T, wavs)
+            eng.solve(noise, n_steps, latent, method)
+            if _on_decoded is None:
+                eng.decode(latent, B * c, T, wavs)
+            else:                                                           # whole clips (all candidates) per chunk
+                step = max(1, int(getattr(self, "decode_chunk_clips", 7))) * c
+                for i0 in range(0, B * c, step):
+                    i1 = min(B * c, i0 + step)
+                    eng.decode(latent[i0:i1], i1 - i0, T, wavs[i0:i1])
+                    _on_decoded(i0, i1, wavs)
         self._last_latent = latent                                          # diagnostics (parity tests, bench gate)
 
         sizes = (batch.sizes * hop).int()                                   # codec.py:91-97

@@ -69,6 +69,33 @@ def all_gather_waveforms(local: torch.Tensor, counts: Sequence[int], group=None)
     return torch.cat(parts, 0)
 
 
+def separate_and_gather(model, batch, noise, counts: Sequence[int], reranking_candidates: int = 1, group=None,
+                        **separate_kwargs) -> torch.Tensor:
+    """separate() of this rank's shard with the waveform all-gather OVERLAPPED with the decode: the codec decodes a few
+    clips at a time and each finished chunk is all-gathered (asynchronously, on NCCL's stream) while the next chunk
+    decodes.  Every rank must hold the same number of clips (`counts` all equal; use separate_sharded otherwise).
+    Returns [sum(counts), 2, S] (candidate 0 of every clip) on every rank."""
+    world = dist.get_world_size(group)
+    B = counts[0]
+    assert all(n == B for n in counts) and len(counts) == world, "separate_and_gather needs equal shards"
+    c = int(reranking_candidates)
+    state = {"buf": None, "works": [], "keep": []}
+
+    def on_decoded(i0, i1, wavs):
+        if state["buf"] is None:
+            state["buf"] = wavs.new_empty(world * B, 2, wavs.shape[-1])
+        b0, b1 = i0 // c, i1 // c                                   # clips of this chunk; their candidate-0 waveforms
+        local = wavs[i0:i1:c].contiguous() if c > 1 else wavs[i0:i1]
+        views = [state["buf"][r * B + b0: r * B + b1] for r in range(world)]
+        state["keep"].append(local)
+        state["works"].append(dist.all_gather(views, local, group=group, async_op=True))
+
+    model.separate(batch, noise=noise, reranking_candidates=c, _on_decoded=on_decoded, **separate_kwargs)
+    for w in state["works"]:
+        w.wait()
+    return state["buf"]
+
+
 def separate_sharded(model, processor, descriptions: List[str], audios: List[torch.Tensor], noise=None,
                      reranking_candidates: int = 1, group=None):
     """Every rank passes the same full clip list; each separates its contiguous shard and all ranks

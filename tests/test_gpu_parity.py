@@ -340,6 +340,33 @@ def test_separate_with_anchors_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
         assert ours.shape == ref.shape and snr_db(ours.cpu(), ref) > 30.0
 
 
+@pytest.mark.parametrize("method,steps", [("euler", 8), ("rk4", 4), ("midpoint", 5)])
+def test_separate_other_fixed_grid_solvers_vs_oracle(tiny_model, tiny_cfg, tiny_sd, method, steps):
+    """The reference forwards **ode_opt to torchdiffeq (model.py:285-290): its other fixed-grid solvers — euler and rk4
+    (the 3/8 rule) — and other step counts, against the oracle's restatement of the same formulas."""
+    from oracle import restate
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.synthetic import (synthetic_clip, synthetic_descriptions, synthetic_noise,
+                                          synthetic_text_features)
+    proc = SAMAudioProcessor(1920, 48000)
+    auds = [synthetic_clip(30 + i, n) for i, n in enumerate([9600, 6000])]
+    desc = synthetic_descriptions(2)
+    host = proc(descriptions=desc, audios=auds)
+    noise = synthetic_noise(2, int(host.sizes.max()))
+    opt = {"method": method, "options": {"step_size": 1.0 / steps}}
+    out = tiny_model.separate(proc(descriptions=desc, audios=auds).to("cuda"), noise=noise.cuda(), ode_opt=opt)
+    tf, tm = synthetic_text_features(desc)
+    tgt, res, lat = restate.separate(tiny_sd, tiny_cfg, host.audios, host.audio_pad_mask, host.sizes, tf, tm,
+                                     host.anchor_ids, host.anchor_alignment, noise, n_steps=steps, method=method,
+                                     return_latent=True)
+    assert rel_l2(tiny_model._last_latent.cpu(), lat) < 2e-2
+    for ours, ref in zip(list(out.target) + list(out.residual), tgt + res):
+        assert ours.shape == ref.shape and snr_db(ours.cpu(), ref) > 30.0
+    with pytest.raises(NotImplementedError):
+        tiny_model.separate(proc(descriptions=desc, audios=auds).to("cuda"), noise=noise.cuda(),
+                            ode_opt={"method": "dopri5"})
+
+
 def test_predict_spans_mutates_batch_but_not_audio(tiny_model):
     """Reference behaviour at the pinned commit (model.py:257-268): predicted spans are written into
     the caller's batch (anchor ids / alignment, bit-exact integers) but the audio is that of the un-anchored batch."""

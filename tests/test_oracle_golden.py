@@ -62,6 +62,19 @@ def test_midpoint_solver_is_32_evaluations_at_exact_times():
     assert abs(float(y[0]) - (1 - 1 / 16 + 0.5 / 256) ** 16) < 1e-6
 
 
+def test_other_fixed_grid_solvers_orders_of_accuracy():
+    """euler / rk4 restatements (torchdiffeq fixed-grid formulas): exact discrete solutions of y' = -y."""
+    import math
+    f = lambda t, y: -y
+    y0 = torch.ones(2, dtype=torch.float64)
+    assert abs(float(restate.odeint_fixed(f, y0, 8, "euler")[0]) - (1 - 1 / 8) ** 8) < 1e-12
+    h = 1 / 4
+    step = 1 - h + h ** 2 / 2 - h ** 3 / 6 + h ** 4 / 24          # any 4th-order RK on a linear ODE
+    assert abs(float(restate.odeint_fixed(f, y0, 4, "rk4")[0]) - step ** 4) < 1e-12
+    assert abs(float(restate.odeint_fixed(f, y0, 4, "rk4")[0]) - math.exp(-1)) < 1e-4
+    assert torch.equal(restate.odeint_fixed(f, y0, 5, "midpoint"), restate.odeint_midpoint(f, y0, 5))
+
+
 def test_separate_control_flow_matches_reference_golden(golden_dir, tiny_cfg, tiny_sd):
     """encode -> 32 evaluations -> decode -> unbatch, candidates 1 and 8 (reference pipeline output)."""
     g = torch.load(os.path.join(golden_dir, "separate_tiny.pt"))

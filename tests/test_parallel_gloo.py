@@ -8,7 +8,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from sam_audio_b200 import SAMAudioProcessor
-from sam_audio_b200.parallel import all_gather_waveforms, broadcast_state_dict, separate_sharded, shard_range
+from sam_audio_b200.parallel import (all_gather_waveforms, broadcast_state_dict, separate_and_gather, separate_sharded,
+                                     shard_range)
 
 
 class _FakeResult:
@@ -22,7 +23,16 @@ class _FakeModel:
     def device(self):
         return torch.device("cpu")
 
-    def separate(self, batch, noise=None, reranking_candidates=1):
+    def separate(self, batch, noise=None, reranking_candidates=1, _on_decoded=None):
+        if _on_decoded is not None:          # chunked decode hook: 2 clips per chunk, c candidates per clip
+            c, B = reranking_candidates, batch.audios.shape[0]
+            wavs = torch.zeros(B * c, 2, 6)
+            for i0 in range(0, B * c, 2 * c):
+                i1 = min(B * c, i0 + 2 * c)
+                for i in range(i0, i1):      # waveform value = 100*rank + clip index, + 0.5 for candidates > 0
+                    wavs[i] = 100.0 * batch.rank + i // c + (0.5 if i % c else 0.0)
+                _on_decoded(i0, i1, wavs)
+            return None
         hop = batch.hop_length
         n = (batch.sizes * hop).int()
         S = int(batch.sizes.max()) * hop
@@ -46,6 +56,13 @@ def _worker(rank, world, port, q):
             exp = torch.zeros(S)
             exp[:n] = float(i + 1)
             ok &= tgt[i].shape == (S,) and torch.equal(tgt[i], 2 * exp) and torch.equal(res[i], -exp)
+        # overlapped gather: every chunk of decoded clips is all-gathered while "decoding" goes on; candidate 0 only
+        for cand in (1, 3):
+            fb = type("B", (), {})()
+            fb.audios, fb.rank = torch.zeros(5, 1, 8), rank
+            full = separate_and_gather(_FakeModel(), fb, None, [5, 5], reranking_candidates=cand)
+            exp = torch.tensor([100.0 * r + i for r in range(world) for i in range(5)])
+            ok &= full.shape == (10, 2, 6) and torch.equal(full[:, 0, 0], exp) and torch.equal(full[:, 1, 5], exp)
         lo, hi = shard_range(3, rank, world)
         local = torch.full((hi - lo, 2, 5), float(rank))
         g = all_gather_waveforms(local, [2, 1])
