@@ -133,6 +133,24 @@ def pick_cpu_threads():
     return best, n
 
 
+def cpu_full_clip(sd, cfg, n_threads: int):
+    """ONE clip through the whole path on the host cores (no extrapolation): encode, all 16 midpoint steps
+    (32 evaluations), decode.  Returns seconds."""
+    from oracle import restate
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_noise, synthetic_text_features
+    torch.set_num_threads(n_threads)
+    torch.set_grad_enabled(False)
+    cc = cfg.audio_codec
+    wav = synthetic_clip(0)[None]
+    tf, tm = synthetic_text_features(["man speaking"])
+    T = wav.shape[-1] // cc.hop_length
+    mask = torch.ones(1, T, dtype=torch.bool)
+    ids, al = restate.process_anchors(None, mask, cc.hop_length, cc.sample_rate)
+    t0 = time.perf_counter()
+    restate.separate(sd, cfg, wav, mask, torch.tensor([float(T)]), tf, tm, ids, al, synthetic_noise(1, T))
+    return time.perf_counter() - t0
+
+
 def cpu_sample(sd, cfg, n_threads: int, repeats: int = 1):
     """One clip of the workload on the host cores through the oracle port (fp32 torch, the reference's
     algorithm): encode once + ONE of the 16 midpoint steps (2 DiT evaluations) + decode target & residual.
@@ -251,6 +269,10 @@ def run_reference(args):
             break
     v = statistics.median([x[0] for x in vals])
     d = vals[0][1]
+    # one un-extrapolated clip (32 evaluations) when the time budget allows: checks the x16 extrapolation of the samples
+    full_s = None
+    if time.perf_counter() - t_start < budget_s - 1.3 / v:
+        full_s = cpu_full_clip(sd, cfg, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": n_warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -259,7 +281,9 @@ def run_reference(args):
         # (one clip of the batch, see cpu_baseline.sample): clips/s does not depend on which clip
         "config": _config(args, max(1, args.gpus), args.batch),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "cores_available": avail, "kind": "port",
-                         "sample": SAMPLE_DESC, "detail_s": d},
+                         "sample": SAMPLE_DESC, "detail_s": d,
+                         "full_clip_s": full_s, "full_clip_note": "one clip through all 32 evaluations, not extrapolated "
+                         "(null: skipped for the time budget); 1/full_clip_s should match `value`"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -341,9 +365,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(batch, noise):
-        if world > 1:       # the all-gather of each decoded chunk runs under the next chunk's decode
+    def gather_step(batch, noise):
+        if args.gather == "overlap":   # the all-gather of each decoded chunk runs under the next chunk's decode
             return separate_and_gather(model, batch, noise, [B] * world, reranking_candidates=C)
+        out = model.separate(batch, noise=noise, reranking_candidates=C)
+        loc = torch.stack([torch.stack([t, r]) for t, r in zip(out.target, out.residual)])
+        return all_gather_waveforms(loc, [B] * world)
+
+    def step_resident(batch, noise):
+        if world > 1:
+            return gather_step(batch, noise)
         return model.separate(batch, noise=noise, reranking_candidates=C)
 
     def step_e2e():
@@ -353,7 +384,7 @@ def run_gpu(args):
         batch = batch.to(dev)                                       # H2D
         nz = noise_host.to(dev, non_blocking=True)
         if world > 1:
-            full = separate_and_gather(model, batch, nz, [B] * world, reranking_candidates=C)
+            full = gather_step(batch, nz)
             loc = full[rank * B:(rank + 1) * B]
         else:
             out = model.separate(batch, noise=nz, reranking_candidates=C)
@@ -373,7 +404,13 @@ def run_gpu(args):
         barrier()
         e0.record()
         for _ in range(k):
-            fn()
+            if os.environ.get("BENCH_DEBUG"):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                print(f"[rank {rank}] step {time.perf_counter() - t0:.3f} s", file=sys.stderr, flush=True)
+            else:
+                fn()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -517,6 +554,8 @@ if __name__ == "__main__":
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: total clips split over the GPUs (overrides --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="overlap", choices=["overlap", "after"],
+                    help="N>1: all-gather each decoded chunk under the next chunk's decode, or once after the decode")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -307,6 +307,7 @@ struct sab_engine {
 
   std::unique_ptr<DitPlan> dit;
   std::map<std::pair<int, long long>, std::unique_ptr<CodecPlan>> enc_plans, dec_plans;
+  int64_t plan_clock = 0;
 
   ~sab_engine();
 };
@@ -1055,7 +1056,19 @@ struct CodecPlan {
   bf16* a_last = nullptr;                                // decoder last-stage activated input
   GemmOp* enc_out = nullptr;                             // in_proj (output pointer patched per chunk)
   double flops = 0;
+  int64_t last_use = 0;
 };
+// A few resident plans per direction (ragged traffic alternates between clip lengths / tail chunks): the least
+// recently used one goes when a new shape arrives and kMaxCodecPlans are resident.
+constexpr size_t kMaxCodecPlans = 3;
+static void evict_codec_plans(sab_engine* e, std::map<std::pair<int, long long>, std::unique_ptr<CodecPlan>>& plans) {
+  if (plans.size() < kMaxCodecPlans) return;
+  SAB_CUDA(cudaDeviceSynchronize());          // the victim's workspace may still be in use by enqueued work
+  auto victim = plans.begin();
+  for (auto it = plans.begin(); it != plans.end(); ++it)
+    if (it->second->last_use < victim->second->last_use) victim = it;
+  plans.erase(victim);
+}
 
 static int pick_bn(int N) {
   if (N % 256 == 0) return 256;
@@ -1126,11 +1139,8 @@ static void plan_resunit(CodecPlan& cp, const ResUnitW& R, int items, long long 
 static CodecPlan* get_enc_plan(sab_engine* e, int items, long long S) {
   auto key = std::make_pair(items, S);
   auto it = e->enc_plans.find(key);
-  if (it != e->enc_plans.end()) return it->second.get();
-  if (!e->enc_plans.empty()) {   // one resident plan per direction: a new clip length replaces the old workspace
-    SAB_CUDA(cudaDeviceSynchronize());
-    e->enc_plans.clear();
-  }
+  if (it != e->enc_plans.end()) { it->second->last_use = ++e->plan_clock; return it->second.get(); }
+  evict_codec_plans(e, e->enc_plans);
   const sab_config& c = e->cfg;
   auto CP = std::make_unique<CodecPlan>();
   CodecPlan& cp = *CP;
@@ -1191,6 +1201,7 @@ static CodecPlan* get_enc_plan(sab_engine* e, int items, long long S) {
     cp.steps.push_back(s2);
   }
   cp.enc_out = &cp.steps.back().op;
+  cp.last_use = ++e->plan_clock;
   CodecPlan* r = CP.get();
   e->enc_plans[key] = std::move(CP);
   return r;
@@ -1199,11 +1210,8 @@ static CodecPlan* get_enc_plan(sab_engine* e, int items, long long S) {
 static CodecPlan* get_dec_plan(sab_engine* e, int items, long long T) {
   auto key = std::make_pair(items, T);
   auto it = e->dec_plans.find(key);
-  if (it != e->dec_plans.end()) return it->second.get();
-  if (!e->dec_plans.empty()) {
-    SAB_CUDA(cudaDeviceSynchronize());
-    e->dec_plans.clear();
-  }
+  if (it != e->dec_plans.end()) { it->second->last_use = ++e->plan_clock; return it->second.get(); }
+  evict_codec_plans(e, e->dec_plans);
   const sab_config& c = e->cfg;
   auto CP = std::make_unique<CodecPlan>();
   CodecPlan& cp = *CP;
@@ -1267,6 +1275,7 @@ static CodecPlan* get_dec_plan(sab_engine* e, int items, long long T) {
   cp.S = Tn;
   { CodecStep s; s.kind = CodecStep::DEC_LAST; cp.steps.push_back(s); }
   cp.flops += 2.0 * items * (double)Tn * C * 7;
+  cp.last_use = ++e->plan_clock;
   CodecPlan* r = CP.get();
   e->dec_plans[key] = std::move(CP);
   return r;

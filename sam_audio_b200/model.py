@@ -68,7 +68,10 @@ class SAMAudio(torch.nn.Module):
         if text_encoder is None:
             text_encoder = T5TextEncoder(cfg.text_encoder, allow_random_init=allow_random_text_encoder)
         self.text_encoder = text_encoder
-        self.vision_encoder = None      # PE-Core-L14 (third party) — SURVEY §8f-2 "next" row
+        # PE-Core-L14-336 (third party, absent): the wrapper — native frame pre-processing + chunked encode — is built;
+        # attach the tower with  model.vision_encoder = PerceptionEncoder(cfg.vision_encoder, model=<CLIP>)
+        from .vision_encoder import PerceptionEncoder
+        self.vision_encoder = PerceptionEncoder(cfg.vision_encoder)
         # PE-A-Frame span predictor (third party, absent here): attach `span_predictor` + `span_predictor_transform`
         # with the reference's call signatures (model.py:96-102) to enable predict_spans=True.
         self.visual_ranker = None       # rerankers are outside the hot path (default config: None)
@@ -262,9 +265,9 @@ class SAMAudio(torch.nn.Module):
         video = None
         if batch.masked_video is not None:
             if self.vision_encoder is None:
-                raise NotImplementedError("visual prompting needs the PE-Core vision encoder "
-                                          "(third-party; SURVEY §8f-2) — attach one as model.vision_encoder")
-            video = self.vision_encoder(batch.masked_video).transpose(1, 2)
+                raise NotImplementedError("visual prompting needs model.vision_encoder (PerceptionEncoder with the "
+                                          "PE-Core tower attached; SURVEY §8f-2)")
+            video = self.vision_encoder(batch.masked_video).transpose(1, 2)   # raises if no tower is attached
         # reference behaviour (model.py:257-268): the forward arguments (anchor tensors included)
         # are bound BEFORE span prediction; predict_spans rebinds batch.anchor_ids/alignment afterwards, so the
         # predicted spans reach the caller's batch but not this call's audio.

@@ -83,7 +83,17 @@ def separate_and_gather(model, batch, noise, counts: Sequence[int], reranking_ca
 
     def on_decoded(i0, i1, wavs):
         if state["buf"] is None:
-            state["buf"] = wavs.new_empty(world * B, 2, wavs.shape[-1])
+            # the gather buffer is kept on the model and reused: a fresh ~1 GB allocation per call would be recorded on
+            # NCCL's stream and force the caching allocator to cudaMalloc / cudaFree (device-synchronising) every step
+            shape = (world * B, 2, wavs.shape[-1])
+            buf = getattr(model, "_gather_buf", None)
+            if buf is None or tuple(buf.shape) != shape or buf.device != wavs.device:
+                buf = wavs.new_empty(*shape)
+                try:
+                    model._gather_buf = buf
+                except Exception:
+                    pass
+            state["buf"] = buf
         b0, b1 = i0 // c, i1 // c                                   # clips of this chunk; their candidate-0 waveforms
         local = wavs[i0:i1:c].contiguous() if c > 1 else wavs[i0:i1]
         views = [state["buf"][r * B + b0: r * B + b1] for r in range(world)]

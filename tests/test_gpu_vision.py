@@ -91,11 +91,14 @@ def test_separate_with_masked_video_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
     masked = proc.mask_videos(vids, masks)
     host = proc(descriptions=desc, audios=auds, masked_videos=masked)
     noise = synthetic_noise(2, int(host.sizes.max()))
-    tiny_model.vision_encoder = PerceptionEncoder(tiny_cfg.vision_encoder, model=tower)
+    prev = tiny_model.vision_encoder                  # the wrapper without a tower: visual prompting must fail loudly
+    with pytest.raises(NotImplementedError):
+        tiny_model.separate(proc(descriptions=desc, audios=auds, masked_videos=masked).to("cuda"), noise=noise.cuda())
+    tiny_model.vision_encoder = PerceptionEncoder(tiny_cfg.vision_encoder, model=tower).cuda()
     try:
         out = tiny_model.separate(proc(descriptions=desc, audios=auds, masked_videos=masked).to("cuda"), noise=noise.cuda())
     finally:
-        tiny_model.vision_encoder = None
+        tiny_model.vision_encoder = prev
     vfeat = restate.vision_encode(host.masked_video, lambda x: tower.encode_image(x, True), tiny_cfg.vision_encoder.image_size,
                                   tiny_cfg.vision_encoder.batch_size).transpose(1, 2)           # [B, dim, T]
     tf, tm = synthetic_text_features(desc)
