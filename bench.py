@@ -257,8 +257,10 @@ def run_reference(args):
     cores, avail = pick_cpu_threads()
     cfg = stand_in_config(args.model)
     sd = make_state_dict(cfg, seed=0)
-    vals = []
     budget_s, t_start = 240.0, time.perf_counter()
+    # one un-extrapolated clip (all 32 evaluations) first: it checks the x16 extrapolation of the bounded samples below
+    full_s = cpu_full_clip(sd, cfg, cores) if args.steps >= 3 else None
+    vals = []
     n_warm = 1 if args.warmup > 0 else 0                    # one untimed pass is enough to warm the CPU path
     n_total = n_warm + args.steps
     for i in range(n_total):
@@ -269,10 +271,6 @@ def run_reference(args):
             break
     v = statistics.median([x[0] for x in vals])
     d = vals[0][1]
-    # one un-extrapolated clip (32 evaluations) when the time budget allows: checks the x16 extrapolation of the samples
-    full_s = None
-    if time.perf_counter() - t_start < budget_s - 1.3 / v:
-        full_s = cpu_full_clip(sd, cfg, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": n_warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -283,7 +281,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "cores_available": avail, "kind": "port",
                          "sample": SAMPLE_DESC, "detail_s": d,
                          "full_clip_s": full_s, "full_clip_note": "one clip through all 32 evaluations, not extrapolated "
-                         "(null: skipped for the time budget); 1/full_clip_s should match `value`"},
+                         "(null: skipped when --steps < 3); 1/full_clip_s should match `value`"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

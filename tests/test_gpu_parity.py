@@ -424,6 +424,43 @@ def test_solver_composition_and_determinism(tiny_model):
     assert rel_l2(a, y0 + f1) < 5e-3
 
 
+def test_exact_softmax_fallback_and_many_anchor_ids(tiny_cfg, tiny_sd, golden_dir, monkeypatch):
+    """(1) Layers whose QK-norm weights do not bound the logits tightly enough run the exact two-pass softmax variant of
+    the tcgen05 attention kernel (forced here through SAB_ATTN_EXACT): same golden as the single-pass path.
+    (2) More anchor ids per clip than the plan's initial table (64) rebuild the plan instead of failing."""
+    from oracle import restate
+    from sam_audio_b200.model import SAMAudio
+    from sam_audio_b200.text_encoder import SyntheticTextEncoder
+    monkeypatch.setenv("SAB_ATTN_EXACT", "1")
+    m = SAMAudio(tiny_cfg, text_encoder=SyntheticTextEncoder())
+    m.load_state_dict(tiny_sd)
+    m = m.eval().cuda()
+    m._ensure_engine()                                     # the env is read when the weights are finalised
+    monkeypatch.delenv("SAB_ATTN_EXACT")
+    g = torch.load(os.path.join(golden_dir, "samaudio_forward_tiny.pt"))
+    out = m.forward(g["noisy"].cuda(), g["feats"].cuda(), g["text"].cuda(), g["time"].cuda(),
+                    masked_video_features=g["video"].cuda(), text_mask=g["text_mask"].cuda(),
+                    anchor_ids=g["anchor_ids"].cuda(), anchor_alignment=g["anchor_alignment"].cuda(),
+                    audio_pad_mask=g["pad_mask"].cuda())
+    assert rel_l2(out.cpu(), g["out"]["video"]) < 2e-2
+    # 70 anchors on one clip -> 72 ids per row (> 64)
+    B, T = 2, 40
+    pad = restate.mask_from_sizes(torch.tensor([40.0, 31.0]))
+    anchors = [[["+" if i % 2 else "-", 0.01 * i, 0.01 * i + 0.05] for i in range(70)], []]
+    ids, al = restate.process_anchors(anchors, pad, 1920, 48000)
+    assert ids.shape[1] == 72
+    gen = torch.Generator().manual_seed(21)
+    noisy = torch.randn(B, T, 256, generator=gen)
+    f = torch.randn(B, T, 128, generator=gen)
+    feats = torch.cat([f, f], 2)
+    text = torch.randn(B, 4, 768, generator=gen)
+    time = torch.tensor([0.125, 0.5])
+    ref = restate.samaudio_forward(tiny_sd, tiny_cfg, noisy, feats, text, time, torch.zeros(B, 1024, T), None, ids, al, pad)
+    out = m.forward(noisy.cuda(), feats.cuda(), text.cuda(), time.cuda(), masked_video_features=torch.zeros(B, 1024, T).cuda(),
+                    anchor_ids=ids.cuda(), anchor_alignment=al.cuda(), audio_pad_mask=pad.cuda())
+    assert rel_l2(out.cpu(), ref) < 2e-2
+
+
 def test_missing_or_unknown_weights_fail_loudly(tiny_cfg, tiny_sd):
     from sam_audio_b200.model import SAMAudio
     from sam_audio_b200.text_encoder import SyntheticTextEncoder
