@@ -72,38 +72,52 @@ def all_gather_waveforms(local: torch.Tensor, counts: Sequence[int], group=None)
 def separate_and_gather(model, batch, noise, counts: Sequence[int], reranking_candidates: int = 1, group=None,
                         **separate_kwargs) -> torch.Tensor:
     """separate() of this rank's shard with the waveform all-gather OVERLAPPED with the decode: the codec decodes a few
-    clips at a time and each finished chunk is all-gathered (asynchronously, on NCCL's stream) while the next chunk
-    decodes.  Every rank must hold the same number of clips (`counts` all equal; use separate_sharded otherwise).
-    Returns [sum(counts), 2, S] (candidate 0 of every clip) on every rank."""
+    clips at a time and each finished chunk is all-gathered (asynchronously, on the collective's own stream) while the
+    next chunk decodes.  Every rank must hold the same number of clips (`counts` all equal; use separate_sharded
+    otherwise).  Returns [sum(counts), 2, S] (candidate 0 of every clip, rank-major) on every rank.
+
+    Buffers are kept on the model and reused: fresh ~GB allocations per call would be recorded on the collective's
+    stream and force the caching allocator into cudaMalloc / cudaFree (device-synchronising) every step — measured: 1.5x
+    step time at N=2.  Each chunk is gathered with all_gather_into_tensor straight into its slice of a staging buffer
+    laid out [chunk][rank][clip] (no temporary), and one strided copy per chunk puts it in rank-major order at the end."""
     world = dist.get_world_size(group)
     B = counts[0]
     assert all(n == B for n in counts) and len(counts) == world, "separate_and_gather needs equal shards"
     c = int(reranking_candidates)
-    state = {"buf": None, "works": [], "keep": []}
+    state = {"stage": None, "out": None, "works": [], "chunks": [], "keep": []}
+
+    def buffers(wavs):
+        S = wavs.shape[-1]
+        cache = getattr(model, "_gather_bufs", None)
+        if cache is None or cache[0].numel() != world * B * 2 * S or cache[0].device != wavs.device:
+            cache = (wavs.new_empty(world * B * 2 * S), wavs.new_empty(world * B, 2, S))
+            try:
+                model._gather_bufs = cache
+            except Exception:
+                pass
+        return cache
 
     def on_decoded(i0, i1, wavs):
-        if state["buf"] is None:
-            # the gather buffer is kept on the model and reused: a fresh ~1 GB allocation per call would be recorded on
-            # NCCL's stream and force the caching allocator to cudaMalloc / cudaFree (device-synchronising) every step
-            shape = (world * B, 2, wavs.shape[-1])
-            buf = getattr(model, "_gather_buf", None)
-            if buf is None or tuple(buf.shape) != shape or buf.device != wavs.device:
-                buf = wavs.new_empty(*shape)
-                try:
-                    model._gather_buf = buf
-                except Exception:
-                    pass
-            state["buf"] = buf
+        if state["stage"] is None:
+            state["stage"], state["out"] = buffers(wavs)
+        S = wavs.shape[-1]
         b0, b1 = i0 // c, i1 // c                                   # clips of this chunk; their candidate-0 waveforms
         local = wavs[i0:i1:c].contiguous() if c > 1 else wavs[i0:i1]
-        views = [state["buf"][r * B + b0: r * B + b1] for r in range(world)]
+        n = (b1 - b0) * 2 * S
+        flat = state["stage"][world * b0 * 2 * S: world * b0 * 2 * S + world * n]
         state["keep"].append(local)
-        state["works"].append(dist.all_gather(views, local, group=group, async_op=True))
+        state["chunks"].append((b0, b1, flat.view(world, b1 - b0, 2, S)))
+        # concatenated form ([world * rows, 2, S]): the one both NCCL and gloo accept
+        state["works"].append(dist.all_gather_into_tensor(flat.view(world * (b1 - b0), 2, S), local, group=group,
+                                                          async_op=True))
 
     model.separate(batch, noise=noise, reranking_candidates=c, _on_decoded=on_decoded, **separate_kwargs)
-    for w in state["works"]:
-        w.wait()
-    return state["buf"]
+    with torch.inference_mode():      # the buffers were created inside separate()'s inference_mode
+        out = state["out"].view(world, B, 2, -1)
+        for w, (b0, b1, dst) in zip(state["works"], state["chunks"]):
+            w.wait()
+            out[:, b0:b1].copy_(dst)
+    return state["out"]
 
 
 def separate_sharded(model, processor, descriptions: List[str], audios: List[torch.Tensor], noise=None,
