@@ -1931,6 +1931,21 @@ static AaTapsDev aa_taps_device(int in_size, int out_size) {   // cached per (de
   return d;
 }
 
+/* host-only test seam: the tap windows / weights the resize kernels use (no GPU needed) */
+int sab_test_aa_taps(int in_size, int out_size, int cap, int* taps, int* lo, int* cnt, float* w) {
+  SAB_API_BEGIN
+  SAB_CHECK(in_size >= 1 && out_size >= 1 && taps && lo && cnt && w, "bad argument");
+  const AaTaps t = aa_taps(in_size, out_size);
+  SAB_CHECK(t.taps <= cap, "tap capacity %d < %d", cap, t.taps);
+  *taps = t.taps;
+  for (int i = 0; i < out_size; ++i) {
+    lo[i] = t.lo[i];
+    cnt[i] = t.cnt[i];
+    for (int j = 0; j < cap; ++j) w[(size_t)i * cap + j] = j < t.taps ? t.w[(size_t)i * t.taps + j] : 0.f;
+  }
+  SAB_API_END
+}
+
 int sab_preprocess_frames(const uint8_t* frames, int n_frames, int H, int W, int out_size, float* workspace, float* out,
                           void* stream) {
   SAB_API_BEGIN

@@ -244,7 +244,6 @@ class SAMAudio(torch.nn.Module):
                  reranking_candidates: int = 1, predict_spans: bool = False, _on_decoded=None) -> SeparationResult:
         """`_on_decoded(i0, i1, wavs)` (private; sam_audio_b200.parallel): called after the waveforms of sequences
         [i0, i1) are enqueued for decoding, so that a collective on them can overlap the next chunk's decode."""
-        eng = self._ensure_engine()
         c = int(reranking_candidates)
         # the reference forwards **ode_opt to torchdiffeq.odeint (model.py:285-290); its fixed-grid solvers are built
         method = ode_opt.get("method", "midpoint")
@@ -258,6 +257,7 @@ class SAMAudio(torch.nn.Module):
         n_steps = round(1.0 / float(step))
         if abs(n_steps * float(step) - 1.0) > 1e-6:
             raise NotImplementedError(f"step_size {step} does not divide [0, 1]")
+        eng = self._ensure_engine()
 
         feats = self._get_audio_features(batch.audios)                      # [B, T, 256]
         text_features, text_mask = self.text_encoder(batch.descriptions)

@@ -121,3 +121,56 @@ def test_t5_bucket_table_matches_transformers_and_hash_tokenizer_is_stable():
     assert torch.equal(a["input_ids"], b["input_ids"]) and torch.equal(a["attention_mask"], b["attention_mask"])
     assert a["input_ids"].shape == (2, 5) and a["input_ids"][0, 2] == 1 and a["input_ids"][0, 3] == 0   # </s>, then pad
     assert a["attention_mask"].sum(1).tolist() == [3, 5]
+
+
+def test_separate_validates_ode_opt_before_touching_the_gpu():
+    """ode_opt is the reference's pass-through to torchdiffeq (model.py:285-290): fixed-grid methods only, and a
+    step_size that divides [0, 1]; the checks run before the engine (and thus a GPU) is needed."""
+    from sam_audio_b200.model import SAMAudio
+    from sam_audio_b200.text_encoder import SyntheticTextEncoder
+    m = SAMAudio(stand_in_config("sam-audio-tiny"), text_encoder=SyntheticTextEncoder())
+    for bad in ({"method": "dopri5"}, {"method": "midpoint"}, {"method": "rk4", "options": {"step_size": 0.3}}):
+        with pytest.raises(NotImplementedError):
+            m.separate(None, ode_opt=bad)
+    with pytest.raises(RuntimeError, match="B200 only|no weights"):      # valid options: next stop is the (absent) engine
+        m.separate(None, ode_opt={"method": "euler", "options": {"step_size": 0.125}})
+
+
+def test_from_pretrained_routes_hub_kwargs(tmp_path, monkeypatch):
+    """Hub keyword arguments (token, cache_dir, revision, ...) go to snapshot_download, config keys override the
+    config, everything else reaches the constructor (reference base.py:17-61 via ModelHubMixin)."""
+    import json
+    import huggingface_hub
+    from sam_audio_b200.model import SAMAudio
+    from sam_audio_b200.synthetic import make_state_dict
+    from sam_audio_b200.text_encoder import SyntheticTextEncoder
+    cfg = stand_in_config("sam-audio-tiny")
+    (tmp_path / "config.json").write_text(json.dumps(cfg.to_dict()))
+    torch.save(make_state_dict(cfg, seed=0), tmp_path / "checkpoint.pt")
+    seen = {}
+
+    def fake_download(repo_id, **kw):
+        seen.update(repo_id=repo_id, **kw)
+        return str(tmp_path)
+    monkeypatch.setattr(huggingface_hub, "snapshot_download", fake_download)
+    m = SAMAudio.from_pretrained("facebook/sam-audio-large", token="t0k", cache_dir="/c", revision="r1", num_anchors=3,
+                                 text_encoder=SyntheticTextEncoder())
+    assert seen == {"repo_id": "facebook/sam-audio-large", "token": "t0k", "cache_dir": "/c", "revision": "r1"}
+    assert isinstance(m.text_encoder, SyntheticTextEncoder) and m._state is not None
+    res = m.load_state_dict(m._state, strict=False)          # no engine yet: nothing to report
+    assert list(res.missing_keys) == [] and list(res.unexpected_keys) == []
+
+
+def test_perception_encoder_wrapper_host_behaviour():
+    from sam_audio_b200.config import PerceptionEncoderConfig
+    from sam_audio_b200.vision_encoder import PerceptionEncoder
+    enc = PerceptionEncoder(PerceptionEncoderConfig())
+    assert enc.batch_size == 300 and enc.image_size == 336 and enc.dim == 1024
+    with pytest.raises(RuntimeError, match="B200 only"):
+        enc.transform(torch.zeros(2, 3, 8, 8, dtype=torch.uint8))            # no CPU path
+    with pytest.raises(NotImplementedError):
+        enc.transform(torch.zeros(2, 3, 8, 8))                               # the reference feeds uint8 frames
+    with pytest.raises(NotImplementedError):
+        enc.encode(torch.zeros(1, 3, 336, 336))                              # no tower attached
+    with pytest.raises(NotImplementedError):
+        PerceptionEncoder(PerceptionEncoderConfig(interpolation_mode="BILINEAR"))

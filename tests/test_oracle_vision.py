@@ -45,3 +45,25 @@ def test_chunked_encode_and_levels_match_reference_golden(golden_dir):
     assert float(out[1, 7:].abs().max()) == 0.0 and float(out[2, 1:].abs().max()) == 0.0     # pad_sequence zeros
     lv = _levels(restate.frame_transform(big)).to(torch.uint8)
     assert float((lv != g["big_levels"]).float().mean()) < 1e-4
+
+
+def test_native_host_tap_tables_equal_the_restatement():
+    """The C++ host code that builds the resize kernels' tap windows and weights (engine.cu aa_taps, exported through
+    the host-only seam sab_test_aa_taps; no GPU involved) against the oracle's float32 restatement: bit-equal."""
+    import ctypes
+    import numpy as np
+    import __graft_entry__ as g
+    g.build()
+    from sam_audio_b200 import _capi
+    lib = _capi.lib()
+    for n_in, n_out in [(640, 336), (360, 336), (36, 336), (336, 336), (1920, 336), (5, 336), (300, 7)]:
+        cap = 256
+        taps = ctypes.c_int(0)
+        lo = np.zeros(n_out, np.int32)
+        cnt = np.zeros(n_out, np.int32)
+        w = np.zeros((n_out, cap), np.float32)
+        _capi.check(lib.sab_test_aa_taps(n_in, n_out, cap, ctypes.addressof(taps), lo.ctypes.data, cnt.ctypes.data, w.ctypes.data))
+        ref = restate._aa_cubic_taps(n_in, n_out)
+        for i, (rlo, rws) in enumerate(ref):
+            assert lo[i] == rlo and cnt[i] == len(rws) <= taps.value
+            assert np.array_equal(w[i, : len(rws)], np.array(rws, np.float32)), (n_in, n_out, i)
