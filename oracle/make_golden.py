@@ -246,6 +246,22 @@ def main():
               f"(lens {[t.numel() for t in r.target]})")
         sep[cand] = dict(target=[t.clone() for t in r.target], residual=[t.clone() for t in r.residual],
                          latent=lat, noise=noise)
+    # candidate selection through an attached text ranker (model.py:316-328): a stand-in with fixed scores — the
+    # call-site logic (argument shapes, argmax, which candidate's waveforms are returned) is the reference's
+    class _FixedRanker(torch.nn.Module):
+        SCORES = torch.tensor([[0.1, 0.9, 0.3], [0.7, 0.2, 0.4]])
+
+        def forward(self, extracted_audio, input_audio, descriptions, sample_rate):
+            assert len(extracted_audio) == 2 and extracted_audio[0].shape[0] == 3 and input_audio[0].shape[0] == 3
+            assert input_audio[1].shape[-1] == extracted_audio[1].shape[-1] and sample_rate == 48000
+            return self.SCORES.clone()
+    model.text_ranker = _FixedRanker()
+    batch = proc(descriptions=desc2, audios=auds2)
+    noise = synthetic.synthetic_noise(2 * 3, int(batch.sizes.max()), seed=777)
+    r = model.separate(batch, noise=noise, reranking_candidates=3)
+    model.text_ranker = None
+    sep["ranked3"] = dict(target=[t.clone() for t in r.target], residual=[t.clone() for t in r.residual], noise=noise,
+                          scores=_FixedRanker.SCORES.clone())
     torch.save(dict(lens=lens2, results=sep), os.path.join(GOLDEN, "separate_tiny.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))

@@ -388,7 +388,7 @@ def vision_encode(videos, encode: Callable, size: int = 336, batch_size: int = 3
 # ----------------------------------------------------------------------------
 def separate(sd: SD, cfg, audios, pad_mask, sizes, text_features, text_mask, anchor_ids,
              anchor_alignment, noise, video_features=None, candidates: int = 1, n_steps: int = 16,
-             return_latent=False, method: str = "midpoint"):
+             return_latent=False, method: str = "midpoint", ranker_scores=None):
     """model.py:247-338 with rankers None (candidate 0; config.py:214-215, model.py:329-330).
     audios [B,1,S] fp32; returns (target list, residual list[, latent])."""
     cc = cfg.audio_codec
@@ -412,6 +412,8 @@ def separate(sd: SD, cfg, audios, pad_mask, sizes, text_features, text_mask, anc
     Bc = lat.shape[0]
     wavs = codec_decode(sd, cc, lat.transpose(1, 2).reshape(2 * Bc, cc.codebook_dim, T)).view(Bc, 2, -1)
     n = (sizes * cc.hop_length).int()                                  # codec.py:91-97
-    tgt = [wavs[b * candidates, 0, : int(n[b])] for b in range(B)]
-    res = [wavs[b * candidates, 1, : int(n[b])] for b in range(B)]
+    # model.py:306-330: arg-max over a ranker's [B, candidates] scores, candidate 0 without a ranker
+    pick = [0] * B if ranker_scores is None else [int(i) for i in ranker_scores.argmax(dim=1)]
+    tgt = [wavs[b * candidates + pick[b], 0, : int(n[b])] for b in range(B)]
+    res = [wavs[b * candidates + pick[b], 1, : int(n[b])] for b in range(B)]
     return (tgt, res, lat) if return_latent else (tgt, res)

@@ -74,8 +74,8 @@ class SAMAudio(torch.nn.Module):
         self.vision_encoder = PerceptionEncoder(cfg.vision_encoder)
         # PE-A-Frame span predictor (third party, absent here): attach `span_predictor` + `span_predictor_transform`
         # with the reference's call signatures (model.py:96-102) to enable predict_spans=True.
-        self.visual_ranker = None       # rerankers are outside the hot path (default config: None)
-        self.text_ranker = None
+        self.visual_ranker = None       # third-party scoring models (default config: None): attach any module honouring
+        self.text_ranker = None         # the contract in sam_audio_b200/ranking.py; selection follows the reference
         self._engine: Optional[_capi.Engine] = None
         self._state: Optional[Dict[str, torch.Tensor]] = None
         self._device = torch.device("cpu")
@@ -297,9 +297,20 @@ class SAMAudio(torch.nn.Module):
         sizes = (batch.sizes * hop).int()                                   # codec.py:91-97
         tgt = self.unbatch(wavs[:, 0].view(B, c, -1), sizes)
         res = self.unbatch(wavs[:, 1].view(B, c, -1), sizes)
-        if c > 1 and (self.visual_ranker is not None or self.text_ranker is not None):
-            raise NotImplementedError("rerankers (CLAP / ImageBind / Judge) are outside the B200 hot path")
-        idxs = [0] * B                                                      # model.py:329-330
+        # candidate selection exactly as the reference (model.py:306-330): visual ranker when there is masked video,
+        # else text ranker, else candidate 0.  The rankers themselves are third-party modules the caller attaches
+        # (sam_audio_b200.ranking documents the contract); the default config has none.
+        if c > 1 and batch.masked_video is not None and self.visual_ranker is not None:
+            scores = self.visual_ranker(extracted_audio=tgt, videos=batch.masked_video, sample_rate=self.sample_rate)
+            idxs = scores.argmax(dim=1)
+        elif c > 1 and self.text_ranker is not None:
+            input_audio = [audio[:, :size].expand(c, -1) for audio, size in zip(batch.audios, sizes)]
+            scores = self.text_ranker(extracted_audio=tgt, input_audio=input_audio, descriptions=batch.descriptions,
+                                      sample_rate=self.sample_rate)
+            idxs = scores.argmax(dim=1)
+        else:
+            idxs = torch.zeros(B, dtype=torch.long, device=noise.device)    # model.py:329-330
+        idxs = [int(i) for i in idxs]
         return SeparationResult(target=[w[i] for w, i in zip(tgt, idxs)],
                                 residual=[w[i] for w, i in zip(res, idxs)], noise=noise)
 

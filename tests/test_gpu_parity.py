@@ -320,6 +320,39 @@ def test_decode_small_chunks_equal_unchunked(tiny_model, monkeypatch):
     assert not torch.equal(small[:, 0], small[:, 1])        # residual is not a copy of the target
 
 
+def test_candidate_selection_through_attached_rankers_vs_reference_golden(tiny_model, golden_dir):
+    """reranking_candidates > 1 with a ranker attached (model.py:306-330): the ranker sees the reference's keyword
+    arguments and the returned waveforms are those of each clip's arg-max candidate — golden = the reference's own
+    separate() with the same fixed-score stand-in ranker (candidates 1 and 0 win for clips 0 and 1)."""
+    from sam_audio_b200 import SAMAudioProcessor
+    from sam_audio_b200.ranking import EnsembleRanker
+    from sam_audio_b200.synthetic import synthetic_clip, synthetic_descriptions
+    g = torch.load(os.path.join(golden_dir, "separate_tiny.pt"))
+    r = g["results"]["ranked3"]
+    proc = SAMAudioProcessor(1920, 48000)
+    auds = [synthetic_clip(i, n) for i, n in enumerate(g["lens"])]
+    seen = {}
+
+    class Fixed(torch.nn.Module):
+        def forward(self, extracted_audio, input_audio, descriptions, sample_rate):
+            seen.update(n=len(extracted_audio), cand=extracted_audio[0].shape[0], inp=input_audio[0].shape,
+                        ext=extracted_audio[0].shape, desc=list(descriptions), sr=sample_rate)
+            return r["scores"].to(extracted_audio[0].device) * 0.5
+    tiny_model.text_ranker = EnsembleRanker([Fixed(), Fixed()], [1.0, 1.0])        # 2 x 0.5 x scores
+    try:
+        out = tiny_model.separate(proc(descriptions=synthetic_descriptions(2), audios=auds).to("cuda"),
+                                  noise=r["noise"].cuda(), reranking_candidates=3)
+    finally:
+        tiny_model.text_ranker = None
+    assert seen["n"] == 2 and seen["cand"] == 3 and seen["sr"] == 48000 and seen["inp"] == seen["ext"]
+    for ours, ref in zip(list(out.target) + list(out.residual), list(r["target"]) + list(r["residual"])):
+        assert ours.shape == ref.shape and snr_db(ours.cpu(), ref) > 30.0
+    # without the ranker candidate 0 is returned: clip 0 differs from the ranked result, clip 1 (winner 0) does not
+    plain = tiny_model.separate(proc(descriptions=synthetic_descriptions(2), audios=auds).to("cuda"),
+                                noise=r["noise"].cuda(), reranking_candidates=3)
+    assert snr_db(plain.target[0].cpu(), r["target"][0]) < 20.0 and torch.equal(plain.target[1], out.target[1])
+
+
 def test_separate_with_anchors_vs_oracle(tiny_model, tiny_cfg, tiny_sd):
     from oracle import restate
     from sam_audio_b200 import SAMAudioProcessor

@@ -174,3 +174,19 @@ def test_perception_encoder_wrapper_host_behaviour():
         enc.encode(torch.zeros(1, 3, 336, 336))                              # no tower attached
     with pytest.raises(NotImplementedError):
         PerceptionEncoder(PerceptionEncoderConfig(interpolation_mode="BILINEAR"))
+
+
+def test_ensemble_ranker_is_the_weighted_sum():
+    from sam_audio_b200.ranking import EnsembleRanker, Ranker
+
+    class A(Ranker):
+        def forward(self, **kw):
+            return torch.tensor([[1.0, 2.0], [3.0, 4.0]]) * kw["k"]
+
+    class B(Ranker):
+        def forward(self, **kw):
+            return torch.tensor([[0.5, 0.0], [0.0, 0.5]])
+    out = EnsembleRanker([A(), B()], [2.0, 4.0])(k=1.0)
+    assert torch.equal(out, torch.tensor([[4.0, 4.0], [6.0, 10.0]]))
+    with pytest.raises(TypeError):
+        Ranker()                                   # abstract, as the reference's

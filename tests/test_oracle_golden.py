@@ -93,6 +93,23 @@ def test_separate_control_flow_matches_reference_golden(golden_dir, tiny_cfg, ti
             assert a.shape == b.shape and rel_l2(a, b) < 1e-4
 
 
+def test_ranked_candidate_selection_matches_reference_golden(golden_dir, tiny_cfg, tiny_sd):
+    """model.py:306-330 with an attached (stand-in, fixed-score) text ranker: arg-max candidate per clip."""
+    g = torch.load(os.path.join(golden_dir, "separate_tiny.pt"))
+    r = g["results"]["ranked3"]
+    auds = [synthetic.synthetic_clip(i, n) for i, n in enumerate(g["lens"])]
+    aud, ws = restate.batch_audio(auds)
+    sizes = restate.wav_to_feature_idx(ws, 1920)
+    mask = restate.mask_from_sizes(sizes)
+    ids, al = restate.process_anchors(None, mask, 1920, 48000)
+    tf, tm = synthetic.synthetic_text_features(synthetic.synthetic_descriptions(2))
+    tgt, res = restate.separate(tiny_sd, tiny_cfg, aud, mask, sizes, tf, tm, ids, al, r["noise"], candidates=3,
+                                ranker_scores=r["scores"])
+    assert r["scores"].argmax(1).tolist() == [1, 0]
+    for a, b in zip(tgt + res, list(r["target"]) + list(r["residual"])):
+        assert a.shape == b.shape and rel_l2(a, b) < 1e-4
+
+
 def test_codec_shapes_and_hop(tiny_cfg, tiny_sd):
     cc = tiny_cfg.audio_codec
     assert cc.hop_length == 1920
