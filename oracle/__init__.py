@@ -32,5 +32,14 @@ Parity status
   codec.py:68) and anything dacvae adds on top of the Descript layout.
 * T5 numerics: the oracle IS ``transformers.T5EncoderModel`` (installed).
   torchdiffeq (absent): fixed-grid midpoint restated, 32 evaluations at exact
-  multiples of 1/32 (model.py:22,285-290).
+  multiples of 1/32 (model.py:22,285-290); euler and rk4 (3/8 rule) restated
+  from the published fixed-grid formulas — PARITY UNPINNED by the reference.
+* Visual prompting front end (vision_encoder.py:47-113): the frame transform is
+  restated from ATen's antialiased bicubic and PINNED twice — against the
+  reference's own PerceptionEncoder class (golden vision.pt, third-party CLIP
+  tower replaced by a stand-in) and against torchvision directly
+  (tests/test_oracle_vision.py: 2-4 uint8 levels in 1e5 differ by one, the rest
+  bit-equal).  The PE-Core tower itself is third-party: unpinned, not built.
+* Candidate selection with attached rankers (model.py:306-330): PINNED by a
+  golden of the reference's separate() with a fixed-score stand-in ranker.
 """
