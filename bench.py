@@ -257,7 +257,7 @@ def run_reference(args):
     cores, avail = pick_cpu_threads()
     cfg = stand_in_config(args.model)
     sd = make_state_dict(cfg, seed=0)
-    budget_s, t_start = 240.0, time.perf_counter()
+    budget_s, t_start = 240.0, time.perf_counter()      # wall budget of this arm, the full clip included
     # one un-extrapolated clip (all 32 evaluations) first: it checks the x16 extrapolation of the bounded samples below
     full_s = cpu_full_clip(sd, cfg, cores) if args.steps >= 3 else None
     vals = []
