@@ -171,6 +171,8 @@ int sab_test_attention_tc2(int items, int heads, int T, const void* q_bf16, cons
  * Engine-independent (no weights). */
 int sab_preprocess_frames(const uint8_t* frames, int n_frames, int H, int W, int out_size, float* workspace, float* out,
                           void* stream);
+/* host-only test seam: evaluation times of sab_solve's grid (method = SAB_ODE_*), in evaluation order */
+int sab_test_solver_grid(int method, int n_steps, int cap, int* n_evals, float* times);
 /* host-only test seam: tap window start / count / normalised weights ([out_size, cap], zero padded) of one axis */
 int sab_test_aa_taps(int in_size, int out_size, int cap, int* taps, int* lo, int* cnt, float* w);
 

@@ -1931,6 +1931,19 @@ static AaTapsDev aa_taps_device(int in_size, int out_size) {   // cached per (de
   return d;
 }
 
+/* host-only test seam: the evaluation times sab_solve uploads for a solver and step count (no GPU needed) */
+int sab_test_solver_grid(int method, int n_steps, int cap, int* n_evals, float* times) {
+  SAB_API_BEGIN
+  SAB_CHECK(n_evals && times && n_steps >= 1, "bad argument");
+  float frac[4];
+  const int S = solver_stages(method, frac);
+  SAB_CHECK(S * n_steps <= cap, "capacity %d < %d", cap, S * n_steps);
+  *n_evals = S * n_steps;
+  for (int k = 0; k < n_steps; ++k)
+    for (int sg = 0; sg < S; ++sg) times[S * k + sg] = ((float)k + frac[sg]) / (float)n_steps;
+  SAB_API_END
+}
+
 /* host-only test seam: the tap windows / weights the resize kernels use (no GPU needed) */
 int sab_test_aa_taps(int in_size, int out_size, int cap, int* taps, int* lo, int* cnt, float* w) {
   SAB_API_BEGIN

@@ -61,3 +61,28 @@ def test_config_struct_layout_matches_header():
     """sizeof(sab_config) from the ctypes mirror == what the C side compiled (13 scalars + 5 + 2x8 ints)."""
     from sam_audio_b200 import _capi
     assert ctypes.sizeof(_capi.SabConfig) == 4 * (13 + 5 + 16)
+
+
+def test_native_solver_grid_matches_the_oracle_evaluation_times(lib):
+    """Host-only seam (no GPU): the evaluation times sab_solve uploads are the ones the oracle's fixed-grid solvers
+    visit, in order — midpoint: exact multiples of 1/32 for 16 steps; euler; rk4 (3/8 rule stages)."""
+    import numpy as np
+    from oracle import restate
+    from sam_audio_b200 import _capi
+    for name, steps in (("midpoint", 16), ("euler", 8), ("rk4", 4), ("midpoint", 5)):
+        seen = []
+
+        def f(t, y):
+            seen.append(float(t))
+            return -y
+        restate.odeint_fixed(f, torch.ones(1), steps, name)
+        n = ctypes.c_int(0)
+        times = np.zeros(128, np.float32)
+        _capi.check(lib.sab_test_solver_grid(_capi.Engine.ODE_METHODS[name], steps, 128, ctypes.addressof(n), times.ctypes.data))
+        assert n.value == len(seen)
+        assert np.allclose(times[: n.value], np.array(seen, np.float32), rtol=0, atol=1e-7), name
+    n = ctypes.c_int(0)
+    times = np.zeros(128, np.float32)
+    _capi.check(lib.sab_test_solver_grid(0, 16, 128, ctypes.addressof(n), times.ctypes.data))
+    assert times[:32].tolist() == [k / 32 for k in range(32)]            # bit-exact multiples of 1/32
+    assert lib.sab_test_solver_grid(7, 4, 128, ctypes.addressof(n), times.ctypes.data) != 0 and b"unknown ODE method" in lib.sab_last_error()
