@@ -190,3 +190,18 @@ def test_ensemble_ranker_is_the_weighted_sum():
     assert torch.equal(out, torch.tensor([[4.0, 4.0], [6.0, 10.0]]))
     with pytest.raises(TypeError):
         Ranker()                                   # abstract, as the reference's
+
+
+def test_bench_parity_gate_logic():
+    """bench.py's parity gate: passes on small deviations, withholds on a wrong result."""
+    import bench
+    g = torch.Generator().manual_seed(0)
+    cpu = dict(features=torch.randn(1, 10, 128, generator=g), velocity=torch.randn(1, 10, 256, generator=g),
+               latent=torch.randn(1, 10, 256, generator=g), wav=torch.randn(2, 1000, generator=g))
+    near = {k: v * (1 + 2e-3) for k, v in cpu.items()}
+    r = bench.parity_gate(near, cpu)
+    assert r["ok"] and abs(r["velocity_rel_l2"] - 2e-3) < 1e-4 and 53 < r["wav_snr_db"] < 55 and r["snr_db"] == r["wav_snr_db"]
+    bad = dict(near, wav=cpu["wav"] + 0.1 * torch.randn(2, 1000, generator=g))
+    assert not bench.parity_gate(bad, cpu)["ok"]
+    bad = dict(near, velocity=-cpu["velocity"])
+    assert not bench.parity_gate(bad, cpu)["ok"]
